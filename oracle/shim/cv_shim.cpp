@@ -1,0 +1,151 @@
+// oracle/shim/cv_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Restates the three OpenCV entry points the reference calls:
+//   cv::GaussianBlur  (helpers.cpp:287,294)  -- the only hot-path arithmetic outside /root/reference
+//   cv::imread        (hesaff.cpp:137)       -- PNM only
+//   cv::SVD 2x2       (hesaff.cpp:117)       -- exporter only
+//
+// GaussianBlur is pinned against the real OpenCV 4.13.0 (cv2, AVX2 dispatch) by
+// tests/test_oracle_blur.py:
+//   * kernel taps: bit-identical to cv2.getGaussianKernel(n, sigma, CV_32F);
+//   * filtered plane: bit-identical to cv2.GaussianBlur(..., BORDER_REPLICATE) for every
+//     column OpenCV's vector loop covers (all but the last `width mod 4` columns, which
+//     OpenCV finishes with differently-rounded scalar code; there the difference is
+//     <= 3.1e-5 on 0..255 data).  We use the vector-loop formula for every column.
+// The operation order below is therefore OpenCV's (RowVec_32f / SymmRowSmallVec_32f and
+// SymmColumnVec_32f with v_muladd == FMA); it was found by experiment, not copied.
+//
+// Build this TU with -mfma -ffp-contract=off: FMAs appear exactly where written.
+#include "cv.h"
+#include <fstream>
+
+namespace cv {
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// getGaussianKernel(n, sigma>0, CV_32F): t_i = exp(-x^2/(2 sigma^2)) in double, summed from the
+// outermost tap inwards, doubled, plus the centre 1; each tap scaled by 1/sum and narrowed to float.
+void shimGaussianKernel(int n, double sigma, float *k)
+{
+   const int R = (n - 1) / 2;
+   const double scale2X = -0.5 / (sigma * sigma);
+   std::vector<double> v(R + 1);
+   double sum = 0;
+   for (int i = 0; i < R; i++) { double x = (double)(i - R); v[i] = exp(scale2X * x * x); sum += v[i]; }
+   v[R] = 1.0;
+   sum = sum * 2 + 1.0;
+   const double m = 1.0 / sum;
+   for (int i = 0; i <= R; i++) k[i] = k[n - 1 - i] = (float)(v[i] * m);
+}
+
+// One filtered row: dst[x] for x in [0,w), replicate border.
+static void rowPass(const float *s, float *d, int w, const float *k, int n)
+{
+   const int R = n / 2;
+   if (n == 1) { for (int x = 0; x < w; x++) d[x] = s[x] * k[0]; return; }
+   // replicate-padded copy so the inner loops are branch free
+   std::vector<float> buf(w + 2 * R);
+   float *p = &buf[R];
+   for (int x = -R; x < w + R; x++) p[x] = s[clampi(x, 0, w - 1)];
+   if (n == 3) {
+      for (int x = 0; x < w; x++) d[x] = __builtin_fmaf(p[x], k[1], (p[x - 1] + p[x + 1]) * k[2]);
+   } else if (n == 5) {
+      for (int x = 0; x < w; x++) {
+         float acc = (p[x - 1] + p[x + 1]) * k[3];
+         acc = __builtin_fmaf(p[x], k[2], acc);
+         d[x] = __builtin_fmaf(p[x - 2] + p[x + 2], k[4], acc);
+      }
+   } else {
+      for (int x = 0; x < w; x++) {
+         float acc = p[x - R] * k[0];
+         for (int i = 1; i < n; i++) acc = __builtin_fmaf(p[x - R + i], k[i], acc);
+         d[x] = acc;
+      }
+   }
+}
+
+void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double sigmaX, double sigmaY, int borderType)
+{
+   (void)borderType; (void)sigmaY;
+   assert(src.type() == CV_32FC1 && ksize.width == ksize.height && (ksize.width & 1));
+   const int h = src.rows, w = src.cols, n = ksize.width, R = n / 2;
+   std::vector<float> k(n);
+   shimGaussianKernel(n, sigmaX, &k[0]);
+
+   // row pass into a temporary (also makes the in-place call safe)
+   std::vector<float> mid((size_t)h * w);
+   for (int y = 0; y < h; y++) rowPass(src.ptr<float>(y), &mid[(size_t)y * w], w, &k[0], n);
+
+   if (dst.data == 0 || dst.rows != h || dst.cols != w || dst.type() != src.type()) dst.create(h, w, src.type());
+   // column pass: centre * k0, then (above + below) fused-multiply-added outwards
+   std::vector<const float *> rowp(h + 2 * R);
+   for (int y = -R; y < h + R; y++) rowp[y + R] = &mid[(size_t)clampi(y, 0, h - 1) * w];
+   for (int y = 0; y < h; y++) {
+      float *d = dst.ptr<float>(y);
+      const float *c = rowp[y + R];
+      for (int x = 0; x < w; x++) d[x] = c[x] * k[R];
+      for (int i = 1; i <= R; i++) {
+         const float *a = rowp[y + R - i], *b = rowp[y + R + i];
+         const float ki = k[R + i];
+         for (int x = 0; x < w; x++) d[x] = __builtin_fmaf(a[x] + b[x], ki, d[x]);
+      }
+   }
+}
+
+Mat imread(const std::string &path)
+{
+   std::ifstream f(path.c_str(), std::ios::binary);
+   if (!f) return Mat();
+   std::string magic;
+   f >> magic;
+   if (magic != "P5" && magic != "P6") return Mat();
+   int vals[3], got = 0;
+   while (got < 3 && f) {
+      int ch = f.peek();
+      if (ch == '#') { std::string line; std::getline(f, line); continue; }
+      if (isspace(ch)) { f.get(); continue; }
+      f >> vals[got++];
+   }
+   f.get(); // single whitespace after maxval
+   if (got < 3 || vals[2] != 255) return Mat();
+   const int w = vals[0], h = vals[1], cn = magic == "P6" ? 3 : 1;
+   std::vector<uchar> raw((size_t)w * h * cn);
+   f.read((char *)&raw[0], raw.size());
+   if ((size_t)f.gcount() != raw.size()) return Mat();
+   Mat m(h, w, CV_8UC3);
+   for (int y = 0; y < h; y++) {
+      uchar *d = m.ptr<uchar>(y);
+      const uchar *s = &raw[(size_t)y * w * cn];
+      for (int x = 0; x < w; x++) {
+         if (cn == 1) { d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = s[x]; }
+         else { d[3 * x] = s[3 * x + 2]; d[3 * x + 1] = s[3 * x + 1]; d[3 * x + 2] = s[3 * x]; } // RGB -> BGR
+      }
+   }
+   return m;
+}
+
+// 2x2 SVD in double via the symmetric eigen-decomposition of A*At; w descending.
+SVD::SVD(const Mat &A, int)
+{
+   const double a = A.at<float>(0, 0), b = A.at<float>(0, 1), c = A.at<float>(1, 0), d = A.at<float>(1, 1);
+   const double p = a * a + b * b, q = a * c + b * d, r = c * c + d * d; // A*At = [p q; q r]
+   const double th = 0.5 * atan2(2 * q, p - r);
+   double cs = cos(th), sn = sin(th);
+   double l1 = p * cs * cs + 2 * q * cs * sn + r * sn * sn;
+   double l2 = p * sn * sn - 2 * q * cs * sn + r * cs * cs;
+   double u00 = cs, u10 = sn, u01 = -sn, u11 = cs;
+   if (l2 > l1) { std::swap(l1, l2); u00 = -sn; u10 = cs; u01 = cs; u11 = sn; }
+   const double s1 = sqrt(l1 > 0 ? l1 : 0), s2 = sqrt(l2 > 0 ? l2 : 0);
+   u = Mat(2, 2, CV_32FC1); w = Mat(2, 1, CV_32FC1); vt = Mat(2, 2, CV_32FC1);
+   u.at<float>(0, 0) = (float)u00; u.at<float>(0, 1) = (float)u01;
+   u.at<float>(1, 0) = (float)u10; u.at<float>(1, 1) = (float)u11;
+   w.at<float>(0, 0) = (float)s1; w.at<float>(1, 0) = (float)s2;
+   // vt = diag(1/w) * ut * A
+   for (int i = 0; i < 2; i++) {
+      const double ui0 = i ? u01 : u00, ui1 = i ? u11 : u10, s = i ? s2 : s1;
+      vt.at<float>(i, 0) = (float)(s > 0 ? (ui0 * a + ui1 * c) / s : 0);
+      vt.at<float>(i, 1) = (float)(s > 0 ? (ui0 * b + ui1 * d) / s : 0);
+   }
+}
+
+} // namespace cv
