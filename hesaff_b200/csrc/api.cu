@@ -1,0 +1,712 @@
+// hesaff_b200/csrc/api.cu -- the C-ABI of include/hesaff_b200.h: context, device-memory plan, launch
+// schedule of the detect -> affine -> describe path (detectPyramidKeypoints, pyramid.cpp:261-292, with the
+// two callbacks of hesaff.cpp:66-105 turned into batch stages).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <fstream>
+#include "common.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+   g_err = msg;
+   return code;
+}
+#define CK(call)                                                                                           \
+   do {                                                                                                    \
+      cudaError_t e_ = (call);                                                                             \
+      if (e_ != cudaSuccess)                                                                               \
+         return fail(HESAFF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+   } while (0)
+
+struct hesaff_ctx {
+   hesaff_params par;
+   int device;
+   int max_w, max_h;
+   int chunk;                  // images resident at once
+   uint32_t cand_cap;          // candidate pool of one chunk
+   int max_cand_per_image;
+   cudaStream_t stream;        // own stream
+   Geom geom;                  // host copy of the current geometry (W,H of the last call)
+   Geom *d_geom;
+   Taps taps0;                 // first blur (pyramid.cpp:278-279)
+   Taps taps[HA_MAX_LVL];      // incremental blurs, level 1..S+1
+   float norm[HA_MAX_LVL];     // sigma_l^2 passed to hessianResponse
+   float lvl_sigma[HA_MAX_LVL];   // curSigma of each level (findLevelKeypoints(curSigma), pyramid.cpp:248)
+   // device memory
+   float *arena; size_t arena_bytes;
+   uint8_t *stage_u8; size_t stage_bytes;
+   uint32_t *mask; size_t mask_words_cap;
+   uint32_t *woff;             // scan of popc(mask): nwords+1
+   uint32_t *scan_tmp; size_t scan_tmp_elems;
+   uint32_t *map; size_t map_elems_cap;
+   Cand cand;
+   uint32_t *det_off, *desc_off;   // cand_cap+1 each
+   Bins bins;
+   int *counters;              // [0] affine work, [1..3] describe work, [4] overflow flag
+   float *scratch; size_t scratch_per_cta; int large_ctas; int maxP;
+   Tables tables;
+   std::vector<void *> table_allocs;
+   // results of the last call
+   int n_images;
+   int *d_ndet, *d_ndesc; size_t counts_cap;
+   std::vector<int> h_ndet, h_ndesc;
+   hesaff_keypoint *d_keys; float *d_ell; size_t keys_cap;
+   uint32_t *d_out_base;       // running total of described keypoints over chunks
+   hesaff_detection *d_dets; size_t dets_cap;
+   int64_t total_desc, total_det;
+   int last_chunks;
+   bool have_result;
+   LaunchCounter lc;
+   // profiling
+   bool profiling;
+   cudaEvent_t ev[8];
+   float stage_ms[6];
+};
+
+extern "C" int hesaff_abi_version(void) { return HESAFF_B200_ABI_VERSION; }
+extern "C" const char *hesaff_last_error(void) { return g_err.c_str(); }
+
+extern "C" int hesaff_params_default(hesaff_params *p)
+{
+   if (!p) return fail(HESAFF_ERR_INVALID, "params is NULL");
+   p->threshold = 16.0f / 3.0f;              // hesaff.cpp:30
+   p->max_iter = 16;                         // hesaff.cpp:31
+   p->desc_factor = 3.0f * sqrtf(3.0f);      // hesaff.cpp:32
+   p->patch_size = 41;                       // hesaff.cpp:33
+   p->verbose = 0;                           // hesaff.cpp:34
+   p->number_of_scales = 3;                  // pyramid.h:35
+   p->initial_sigma = 1.6f;                  // pyramid.h:36
+   p->edge_eigenvalue_ratio = 10.0f;         // pyramid.h:38
+   p->border = 5;                            // pyramid.h:39
+   p->convergence_threshold = 0.05f;         // affine.h:41
+   p->smm_window_size = 19;                  // affine.h:43
+   p->max_octaves = 0;
+   return HESAFF_OK;
+}
+
+// ---- host-side constant tables (glibc libm, same expressions as the reference) ---------------------
+static int blur_size(float sigma)
+{
+   int size = (int)(2.0 * 3.0 * sigma + 1.0);   // helpers.cpp:286
+   if (size % 2 == 0) size++;
+   return size;
+}
+
+// cv::getGaussianKernel(n, sigma, CV_32F) as OpenCV 4.x evaluates it (pinned in tests/test_oracle_blur.py)
+static void gauss_kernel(int n, double sigma, std::vector<float> &k)
+{
+   const int R = (n - 1) / 2;
+   const double scale2X = -0.5 / (sigma * sigma);
+   std::vector<double> v(R + 1);
+   double sum = 0;
+   for (int i = 0; i < R; i++) { double x = (double)(i - R); v[i] = exp(scale2X * x * x); sum += v[i]; }
+   v[R] = 1.0;
+   sum = sum * 2 + 1.0;
+   const double m = 1.0 / sum;
+   k.resize(n);
+   for (int i = 0; i <= R; i++) k[i] = k[n - 1 - i] = (float)(v[i] * m);
+}
+
+static int make_taps(float sigma, Taps &t)
+{
+   const int n = blur_size(sigma);
+   if (n > HA_MAX_TAPS) return -1;
+   std::vector<float> k;
+   gauss_kernel(n, (double)sigma, k);
+   t.n = n;
+   memset(t.k, 0, sizeof(t.k));
+   for (int i = 0; i < n; i++) t.k[i] = k[i];
+   return 0;
+}
+
+// computeGaussMask, helpers.cpp:104-129
+static void smm_mask(float *mask, int size)
+{
+   int halfSize = size >> 1;
+   float scale = float(halfSize) / 3.0f;
+   float scale2 = -2.0f * scale * scale;
+   std::vector<float> tmp(halfSize + 1);
+   for (int i = 0; i <= halfSize; i++) tmp[i] = expf((float(i * i) / scale2));
+   int endSize = int(ceilf(scale * 5.0f) - halfSize);
+   for (int i = 1; i < endSize; i++) tmp[halfSize - i] += expf((float((i + halfSize) * (i + halfSize)) / scale2));
+   for (int i = 0; i <= halfSize; i++)
+      for (int j = 0; j <= halfSize; j++) {
+         float v = tmp[i] * tmp[j];
+         mask[(i + halfSize) * size + (-j + halfSize)] = v;
+         mask[(-i + halfSize) * size + (j + halfSize)] = v;
+         mask[(i + halfSize) * size + (j + halfSize)] = v;
+         mask[(-i + halfSize) * size + (-j + halfSize)] = v;
+      }
+}
+
+// computeCircularGaussMask, helpers.cpp:131-147
+static void sift_mask(float *mask, int size)
+{
+   int halfSize = size >> 1;
+   float r2 = float(halfSize * halfSize);
+   float sigma2 = 0.9f * r2;
+   float *mp = mask;
+   for (int i = 0; i < size; i++)
+      for (int j = 0; j < size; j++) {
+         float disq = float((i - halfSize) * (i - halfSize) + (j - halfSize) * (j - halfSize));
+         *mp++ = (disq < r2) ? expf(-disq / sigma2) : 0;
+      }
+}
+
+template <typename T> static int upload(hesaff_ctx *c, const std::vector<T> &h, const T **d)
+{
+   void *p = nullptr;
+   CK(cudaMalloc(&p, std::max<size_t>(sizeof(T) * h.size(), 16)));
+   c->table_allocs.push_back(p);
+   CK(cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+   *d = (const T *)p;
+   return HESAFF_OK;
+}
+
+static int build_tables(hesaff_ctx *c)
+{
+   std::vector<float> m19(HA_SMM_PX), m41(HA_PATCH_PX);
+   smm_mask(m19.data(), HA_SMM);
+   sift_mask(m41.data(), HA_PATCH);
+   int rc;
+   if ((rc = upload(c, m19, &c->tables.smm_mask))) return rc;
+   if ((rc = upload(c, m41, &c->tables.sift_mask))) return rc;
+   // per-patch blur kernels, indexed by m = (P0-1)/2; the patch must fit in the image so P0 <= min(W,H)
+   const int maxP0 = std::min(c->max_w, c->max_h) + 4;
+   const int count = maxP0 / 2 + 2;
+   std::vector<int> pn(count, 1), poff(count, 0);
+   std::vector<float> pk;
+   for (int m = 0; m < count; m++) {
+      const int P0 = 2 * m + 1;
+      const float its = float(P0) / float(HA_PATCH);     // affine.cpp:109
+      const float sigma = 1.5f * its;                     // affine.cpp:129
+      const int n = blur_size(sigma);
+      std::vector<float> k;
+      gauss_kernel(n, (double)sigma, k);
+      pn[m] = n;
+      poff[m] = (int)pk.size();
+      for (int i = n / 2; i < n; i++) pk.push_back(k[i]);
+      if (n / 2 > 255) return fail(HESAFF_ERR_INVALID, "image too large for the per-patch blur table");
+   }
+   c->tables.pk_count = count;
+   if ((rc = upload(c, pn, &c->tables.pk_n))) return rc;
+   if ((rc = upload(c, poff, &c->tables.pk_off))) return rc;
+   if ((rc = upload(c, pk, &c->tables.pk))) return rc;
+   return HESAFF_OK;
+}
+
+// ---- geometry / memory plan ------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int plan_geometry(const hesaff_params &p, int W, int H, Geom &g)
+{
+   memset(&g, 0, sizeof(g));
+   g.W = W; g.H = H; g.S = p.number_of_scales; g.border = p.border;
+   // octave loop of detectPyramidKeypoints, pyramid.cpp:283-291
+   const int minSize = 2 * p.border + 2;
+   int rows = H, cols = W, o = 0;
+   while (rows > minSize && cols > minSize) {
+      if (p.max_octaves > 0 && o >= p.max_octaves) break;
+      if (o >= HA_MAX_OCT) break;
+      g.w[o] = cols; g.h[o] = rows; g.pitch[o] = (int)align_up(cols, 4);
+      rows /= 2; cols /= 2; o++;       // halfImage, helpers.cpp:333
+   }
+   g.nOct = o;
+   size_t off = 0;
+   g.img_off = off;
+   off += align_up((size_t)H * align_up(W, 4), 64);
+   if (g.nOct == 0) g.pitch[0] = (int)align_up(W, 4);
+   for (o = 0; o < g.nOct; o++)
+      for (int l = 0; l < g.S + 2; l++) {
+         g.L_off[o][l] = off; off += align_up((size_t)g.h[o] * g.pitch[o], 64);
+         g.R_off[o][l] = off; off += align_up((size_t)g.h[o] * g.pitch[o], 64);
+      }
+   g.arena_stride = off;
+   size_t mo = 0, po = 0;
+   for (o = 0; o < g.nOct; o++) {
+      g.wpr[o] = (g.w[o] + 31) / 32;
+      g.mask_oct_off[o] = mo;
+      for (int l = 1; l <= g.S; l++) { g.mask_off[o][l] = mo; mo += (size_t)g.h[o] * g.wpr[o]; }
+      g.map_off[o] = po; po += (size_t)g.h[o] * g.w[o];
+   }
+   g.mask_oct_off[g.nOct] = mo;
+   g.mask_stride = mo;
+   g.map_stride = po;
+   // thresholds, pyramid.h:57-64
+   g.edgeScoreThreshold = (p.edge_eigenvalue_ratio + 1.0f) * (p.edge_eigenvalue_ratio + 1.0f) / p.edge_eigenvalue_ratio;
+   g.finalThreshold = p.threshold * p.threshold;
+   g.positiveThreshold = (float)(0.8 * g.finalThreshold);
+   g.negativeThreshold = -g.positiveThreshold;
+   g.initialSigma = p.initial_sigma; g.mrSize = p.desc_factor; g.convergenceThreshold = p.convergence_threshold;
+   g.maxIterations = p.max_iter;
+   return HESAFF_OK;
+}
+
+static size_t per_image_bytes(const Geom &g, int max_cand)
+{
+   return g.arena_stride * 4 + (size_t)g.W * g.H + g.mask_stride * 8 + g.map_stride * 4 + (size_t)max_cand * 260;
+}
+
+template <typename T> static int dmalloc(T **p, size_t n)
+{
+   void *q = nullptr;
+   CK(cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256)));
+   *p = (T *)q;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int device, int max_width, int max_height,
+                             int max_batch, int max_candidates_per_image)
+{
+   if (!out || !p) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   *out = nullptr;
+   if (p->patch_size != HA_PATCH) return fail(HESAFF_ERR_INVALID, "only patch_size == 41 is supported");
+   if (p->smm_window_size != HA_SMM) return fail(HESAFF_ERR_INVALID, "only smm_window_size == 19 is supported");
+   if (p->number_of_scales < 1 || p->number_of_scales + 2 > HA_MAX_LVL) return fail(HESAFF_ERR_INVALID, "number_of_scales out of range [1,12]");
+   if (p->border < 2) return fail(HESAFF_ERR_INVALID, "border must be >= 2 (pyramid.cpp:208)");
+   if (p->max_iter < 1) return fail(HESAFF_ERR_INVALID, "max_iter must be >= 1");
+   if (max_width < 1 || max_height < 1 || max_width >= (1 << 20) || max_height >= (1 << 20)) return fail(HESAFF_ERR_INVALID, "bad max size");
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(HESAFF_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+   if (device < 0 || device >= ndev) return fail(HESAFF_ERR_INVALID, "bad device index");
+   CK(cudaSetDevice(device));
+   cudaDeviceProp prop;
+   CK(cudaGetDeviceProperties(&prop, device));
+   if (prop.major < 10) return fail(HESAFF_ERR_CUDA, "device is not sm_100 class (kernels are compiled for sm_100a only)");
+
+   hesaff_ctx *c = new hesaff_ctx();
+   c->par = *p; c->device = device; c->max_w = max_width; c->max_h = max_height;
+   c->have_result = false; c->profiling = false; c->lc.n = 0;
+   c->d_dets = nullptr; c->dets_cap = 0; c->d_keys = nullptr; c->d_ell = nullptr; c->keys_cap = 0;
+   c->d_ndet = c->d_ndesc = nullptr; c->counts_cap = 0;
+   memset(c->stage_ms, 0, sizeof(c->stage_ms));
+   *out = c;   // so that a failed create can still be destroyed
+
+   // scale-space constants with the reference's float operations (pyramid.cpp:227-240,257,278)
+   {
+      float curSigma0 = 0.5f;
+      c->taps0.n = 0;
+      if (p->initial_sigma > curSigma0) {
+         float sigma = sqrtf(p->initial_sigma * p->initial_sigma - curSigma0 * curSigma0);
+         if (make_taps(sigma, c->taps0)) return fail(HESAFF_ERR_INVALID, "initial blur needs more than 33 taps");
+      }
+      const int S = p->number_of_scales;
+      float sigmaStep = powf(2.0f, 1.0f / (float)S);
+      float curSigma = p->initial_sigma;
+      c->norm[0] = curSigma * curSigma;
+      c->lvl_sigma[0] = curSigma;
+      for (int i = 1; i < S + 2; i++) {
+         float sigma = curSigma * sqrtf(sigmaStep * sigmaStep - 1.0f);
+         if (make_taps(sigma, c->taps[i])) return fail(HESAFF_ERR_INVALID, "a pyramid blur needs more than 33 taps");
+         sigma = curSigma * sigmaStep;
+         c->norm[i] = sigma * sigma;
+         curSigma *= sigmaStep;
+         c->lvl_sigma[i] = curSigma;
+      }
+   }
+   Geom g;
+   plan_geometry(*p, max_width, max_height, g);
+   c->max_cand_per_image = max_candidates_per_image > 0 ? max_candidates_per_image
+                                                        : std::max(4096, (int)(((size_t)max_width * max_height) / 10));
+   size_t free_b = 0, total_b = 0;
+   CK(cudaMemGetInfo(&free_b, &total_b));
+   const size_t pib = per_image_bytes(g, c->max_cand_per_image);
+   int chunk = max_batch;
+   if (chunk <= 0) chunk = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(free_b * 0.5) / pib));
+   if ((size_t)chunk * pib > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");
+   c->chunk = chunk;
+   if ((size_t)chunk * c->max_cand_per_image >= 0xFFFFFFF0ull) return fail(HESAFF_ERR_INVALID, "candidate pool exceeds 32-bit indexing");
+   c->cand_cap = (uint32_t)((size_t)chunk * c->max_cand_per_image);
+
+   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
+   int rc;
+   if ((rc = build_tables(c))) return rc;
+   if ((rc = dmalloc(&c->d_geom, 1))) return rc;
+   c->arena_bytes = g.arena_stride * 4 * chunk;
+   if ((rc = dmalloc(&c->arena, g.arena_stride * chunk))) return rc;
+   c->stage_bytes = (size_t)max_width * max_height * 4 * chunk;   // u8 or f32 host input staging
+   if ((rc = dmalloc(&c->stage_u8, c->stage_bytes))) return rc;
+   c->mask_words_cap = g.mask_stride * chunk;
+   if ((rc = dmalloc(&c->mask, c->mask_words_cap + 1))) return rc;
+   if ((rc = dmalloc(&c->woff, c->mask_words_cap + 2))) return rc;
+   c->scan_tmp_elems = std::max(ha_scan_tmp_elems(c->mask_words_cap), ha_scan_tmp_elems(c->cand_cap)) + 8;
+   if ((rc = dmalloc(&c->scan_tmp, c->scan_tmp_elems))) return rc;
+   c->map_elems_cap = g.map_stride * chunk;
+   if ((rc = dmalloc(&c->map, c->map_elems_cap + 1))) return rc;
+   const size_t cc = c->cand_cap;
+   if ((rc = dmalloc(&c->cand.key, cc))) return rc;
+   if ((rc = dmalloc(&c->cand.x, cc)) || (rc = dmalloc(&c->cand.y, cc)) || (rc = dmalloc(&c->cand.s, cc)) ||
+       (rc = dmalloc(&c->cand.response, cc)) || (rc = dmalloc(&c->cand.cell, cc)) || (rc = dmalloc(&c->cand.type, cc)) ||
+       (rc = dmalloc(&c->cand.flags, cc)) || (rc = dmalloc(&c->cand.U, cc)) || (rc = dmalloc(&c->cand.A, cc)) ||
+       (rc = dmalloc(&c->cand.iters, cc)) || (rc = dmalloc(&c->cand.desc, cc * 128)))
+      return rc;
+   if ((rc = dmalloc(&c->det_off, cc + 2)) || (rc = dmalloc(&c->desc_off, cc + 2))) return rc;
+   for (int b = 0; b < 3; b++)
+      if ((rc = dmalloc(&c->bins.list[b], cc))) return rc;
+   if ((rc = dmalloc(&c->bins.count, 4))) return rc;
+   if ((rc = dmalloc(&c->counters, 8))) return rc;
+   if ((rc = dmalloc(&c->d_out_base, 2))) return rc;
+   c->maxP = std::min(max_width, max_height) + 8;
+   c->large_ctas = 148 * 2;
+   c->scratch_per_cta = align_up((size_t)c->maxP * 82, 64);
+   if ((rc = dmalloc(&c->scratch, c->scratch_per_cta * c->large_ctas))) return rc;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_destroy(hesaff_ctx *c)
+{
+   if (!c) return HESAFF_OK;
+   cudaSetDevice(c->device);
+   if (c->stream) cudaStreamSynchronize(c->stream);
+   void *ptrs[] = {c->d_geom, c->arena, c->stage_u8, c->mask, c->woff, c->scan_tmp, c->map, c->cand.key, c->cand.x,
+                   c->cand.y, c->cand.s, c->cand.response, c->cand.cell, c->cand.type, c->cand.flags, c->cand.U,
+                   c->cand.A, c->cand.iters, c->cand.desc, c->det_off, c->desc_off, c->bins.list[0], c->bins.list[1],
+                   c->bins.list[2], c->bins.count, c->counters, c->d_out_base, c->scratch, c->d_ndet, c->d_ndesc,
+                   c->d_keys, c->d_ell, c->d_dets};
+   for (void *p : ptrs) if (p) cudaFree(p);
+   for (void *p : c->table_allocs) cudaFree(p);
+   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+   if (c->stream) cudaStreamDestroy(c->stream);
+   delete c;
+   return HESAFF_OK;
+}
+
+// ---- the hot path ------------------------------------------------------------------------------------
+__global__ void k_add_total(uint32_t *base, const uint32_t *add) { *base += *add; }
+
+static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int W, int H, size_t row_pitch,
+                       size_t img_stride, int on_device, void *stream_)
+{
+   if (!c) return fail(HESAFF_ERR_INVALID, "ctx is NULL");
+   if (!images || n < 0 || W < 1 || H < 1) return fail(HESAFF_ERR_INVALID, "bad image arguments");
+   if (W > c->max_w || H > c->max_h) return fail(HESAFF_ERR_INVALID, "image larger than the context was created for");
+   const size_t esz = is_u8 ? 1 : 4;
+   if (row_pitch < (size_t)W * esz || img_stride < row_pitch * (size_t)(H - 1) + (size_t)W * esz)
+      return fail(HESAFF_ERR_INVALID, "row pitch / image stride too small");
+   CK(cudaSetDevice(c->device));
+   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : c->stream;
+   c->have_result = false;
+
+   Geom &g = c->geom;
+   plan_geometry(c->par, W, H, g);
+   for (int l = 0; l < g.S + 2; l++) g.sigma[l] = c->lvl_sigma[l];
+   CK(cudaMemcpyAsync(c->d_geom, &g, sizeof(Geom), cudaMemcpyHostToDevice, st));
+
+   // output buffers for the whole batch
+   if ((size_t)n > c->counts_cap || !c->d_ndet) {
+      if (c->d_ndet) cudaFree(c->d_ndet);
+      if (c->d_ndesc) cudaFree(c->d_ndesc);
+      c->d_ndet = c->d_ndesc = nullptr;
+      int rc;
+      if ((rc = dmalloc(&c->d_ndet, (size_t)n + 1)) || (rc = dmalloc(&c->d_ndesc, (size_t)n + 1))) return rc;
+      c->counts_cap = n;
+   }
+   const size_t want_keys = std::max<size_t>(1024, (size_t)n * (size_t)(c->max_cand_per_image / 2));
+   if (want_keys > c->keys_cap) {
+      if (c->d_keys) cudaFree(c->d_keys);
+      if (c->d_ell) cudaFree(c->d_ell);
+      c->d_keys = nullptr; c->d_ell = nullptr;
+      int rc;
+      if ((rc = dmalloc(&c->d_keys, want_keys)) || (rc = dmalloc(&c->d_ell, want_keys * 5))) return rc;
+      c->keys_cap = want_keys;
+   }
+   CK(cudaMemsetAsync(c->d_ndet, 0, sizeof(int) * ((size_t)n + 1), st));
+   CK(cudaMemsetAsync(c->d_ndesc, 0, sizeof(int) * ((size_t)n + 1), st));
+   CK(cudaMemsetAsync(c->d_out_base, 0, sizeof(uint32_t) * 2, st));
+   CK(cudaMemsetAsync(c->counters + 4, 0, sizeof(int), st));
+   memset(c->stage_ms, 0, sizeof(c->stage_ms));
+   c->n_images = n;
+   c->last_chunks = 0;
+   const int S = g.S;
+
+   for (int start = 0; start < n; start += c->chunk) {
+      const int cn = std::min(c->chunk, n - start);
+      c->last_chunks++;
+      if (c->profiling) cudaEventRecord(c->ev[0], st);
+      // ---- stage 0: upload + gray float image (hesaff.cpp:138-148) ---------------------------------
+      const char *src = (const char *)images + (size_t)start * img_stride;
+      const void *dsrc = src;
+      size_t d_row_pitch = row_pitch, d_img_stride = img_stride;
+      if (!on_device) {
+         d_row_pitch = (size_t)W * esz; d_img_stride = d_row_pitch * H;
+         if (row_pitch == d_row_pitch && img_stride == d_img_stride)
+            CK(cudaMemcpyAsync(c->stage_u8, src, d_img_stride * cn, cudaMemcpyHostToDevice, st));
+         else
+            for (int i = 0; i < cn; i++)
+               CK(cudaMemcpy2DAsync(c->stage_u8 + (size_t)i * d_img_stride, d_row_pitch, src + (size_t)i * img_stride,
+                                    row_pitch, d_row_pitch, H, cudaMemcpyHostToDevice, st));
+         dsrc = c->stage_u8;
+      }
+      float *img_plane = c->arena + g.img_off;
+      if (is_u8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
+      else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
+      if (c->profiling) cudaEventRecord(c->ev[1], st);
+
+      // ---- stage 1: pyramid (pyramid.cpp:261-292, 224-259) ------------------------------------------
+      if (g.nOct > 0) {
+         float *L00 = c->arena + g.L_off[0][0], *R00 = c->arena + g.R_off[0][0];
+         if (c->taps0.n > 0) {
+            if (ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0],
+                               c->taps0, cn, st, c->lc))
+               return fail(HESAFF_ERR_INVALID, "unsupported blur size");
+         } else {
+            Taps id; id.n = 1; memset(id.k, 0, sizeof(id.k)); id.k[0] = 1.0f;   // firstLevel = image.clone()
+            ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0], id,
+                           cn, st, c->lc);
+         }
+      }
+      for (int o = 0; o < g.nOct; o++) {
+         if (o > 0)   // response of the decimated first level (cur = hessianResponse(blur, sigma0^2), pyramid.cpp:230)
+            ha_launch_hessian(c->arena + g.L_off[o][0], c->arena + g.R_off[o][0], g.w[o], g.h[o], g.pitch[o], g.arena_stride,
+                              c->norm[0], cn, st, c->lc);
+         for (int i = 1; i < S + 2; i++) {
+            const bool seed_next = (i == S) && (o + 1 < g.nOct);   // halfImage(nextBlur) at i == numberOfScales
+            float *half = seed_next ? c->arena + g.L_off[o + 1][0] : nullptr;
+            if (ha_launch_blur(c->arena + g.L_off[o][i - 1], c->arena + g.L_off[o][i], c->arena + g.R_off[o][i], half, g.w[o],
+                               g.h[o], g.pitch[o], seed_next ? g.w[o + 1] : 0, seed_next ? g.h[o + 1] : 0,
+                               seed_next ? g.pitch[o + 1] : 0, g.arena_stride, c->norm[i], c->taps[i], cn, st, c->lc))
+               return fail(HESAFF_ERR_INVALID, "unsupported blur size");
+         }
+      }
+      if (c->profiling) cudaEventRecord(c->ev[2], st);
+
+      // ---- stage 2: extrema, ordered compaction, localisation, dedup ------------------------------------
+      const size_t nwords = g.mask_stride * cn;
+      ha_launch_nms(c->arena, g, c->d_geom, c->mask, cn, st, c->lc);
+      ha_launch_scan_popc(c->mask, nwords, c->woff, c->scan_tmp, st, c->lc);
+      const uint32_t *d_count = c->woff + nwords;   // number of candidates in this chunk
+      ha_launch_expand(c->mask, c->woff, c->d_geom, nwords, c->cand, c->cand_cap, c->counters + 4, st, c->lc);
+      CK(cudaMemsetAsync(c->map, 0xFF, sizeof(uint32_t) * g.map_stride * cn, st));
+      ha_launch_localize(c->arena, c->d_geom, c->cand, d_count, c->cand_cap, c->map, st, c->lc);
+      if (c->profiling) cudaEventRecord(c->ev[3], st);
+
+      // ---- stage 3: affine shape ---------------------------------------------------------------------
+      CK(cudaMemsetAsync(c->counters, 0, sizeof(int) * 4, st));
+      CK(cudaMemsetAsync(c->bins.count, 0, sizeof(int) * 4, st));
+      ha_launch_affine(c->arena, c->d_geom, c->tables, c->cand, d_count, c->cand_cap, c->map, c->d_ndet + start, c->bins,
+                       c->counters, st, c->lc);
+      if (c->profiling) cudaEventRecord(c->ev[4], st);
+
+      // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
+      ha_launch_describe(c->arena, c->d_geom, c->tables, c->cand, c->bins, c->counters + 1, c->scratch, c->scratch_per_cta,
+                         c->large_ctas, c->maxP, nullptr, 0, nullptr, st, c->lc);
+      if (c->profiling) cudaEventRecord(c->ev[5], st);
+
+      // ---- stage 5: ordered compaction into Keypoint records -------------------------------------------
+      ha_launch_scan_flags(c->cand.flags, HA_F_DESC, d_count, c->cand_cap, c->desc_off, c->scan_tmp, st, c->lc);
+      // records of this chunk start at the running total of the previous chunks (device-side base)
+      ha_launch_compact(c->cand, d_count, c->cand_cap, c->desc_off, c->d_geom, c->d_keys, c->d_ell, c->d_ndesc + start,
+                        c->d_out_base, (uint32_t)std::min<size_t>(c->keys_cap, 0xFFFFFFFFu), c->counters + 4, st, c->lc);
+      k_add_total<<<1, 1, 0, st>>>(c->d_out_base, c->desc_off + c->cand_cap);
+      c->lc.n++;
+      if (c->profiling) {
+         cudaEventRecord(c->ev[6], st);
+         CK(cudaEventSynchronize(c->ev[6]));
+         for (int k = 0; k < 6; k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]);
+            c->stage_ms[k] += ms;
+         }
+      }
+   }
+   // counts to the host; this is the only synchronisation point of a single-chunk call
+   c->h_ndet.assign(n, 0); c->h_ndesc.assign(n, 0);
+   int overflow = 0;
+   uint32_t total = 0;
+   if (n > 0) {
+      CK(cudaMemcpyAsync(c->h_ndet.data(), c->d_ndet, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(c->h_ndesc.data(), c->d_ndesc, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+   }
+   CK(cudaMemcpyAsync(&overflow, c->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+   CK(cudaMemcpyAsync(&total, c->d_out_base, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CK(cudaStreamSynchronize(st));
+   CK(cudaGetLastError());
+   if (overflow) return fail(HESAFF_ERR_CAPACITY, "candidate pool / keypoint buffer overflow; raise max_candidates_per_image");
+   if (total > c->keys_cap) return fail(HESAFF_ERR_CAPACITY, "keypoint output buffer overflow; raise max_candidates_per_image");
+   c->total_desc = total;
+   c->total_det = 0;
+   for (int i = 0; i < n; i++) c->total_det += c->h_ndet[i];
+   c->have_result = true;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_detect_u8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
+                                size_t image_stride_bytes, int on_device, void *stream)
+{
+   return detect_impl(ctx, images, true, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+}
+
+extern "C" int hesaff_detect_f32(hesaff_ctx *ctx, const float *images, int n, int width, int height, size_t row_pitch_bytes,
+                                 size_t image_stride_bytes, int on_device, void *stream)
+{
+   return detect_impl(ctx, images, false, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+}
+
+// ---- results -------------------------------------------------------------------------------------------
+#define NEED_RESULT(c)                                                                           \
+   do {                                                                                          \
+      if (!(c)) return fail(HESAFF_ERR_INVALID, "ctx is NULL");                                  \
+      if (!(c)->have_result) return fail(HESAFF_ERR_STATE, "no successful hesaff_detect_* yet"); \
+      CK(cudaSetDevice((c)->device));                                                            \
+   } while (0)
+
+extern "C" int hesaff_result_counts(hesaff_ctx *c, int *n_detected, int *n_described)
+{
+   NEED_RESULT(c);
+   if (n_detected) memcpy(n_detected, c->h_ndet.data(), sizeof(int) * c->n_images);
+   if (n_described) memcpy(n_described, c->h_ndesc.data(), sizeof(int) * c->n_images);
+   return HESAFF_OK;
+}
+
+extern "C" int64_t hesaff_result_total(hesaff_ctx *c)
+{
+   if (!c || !c->have_result) return fail(HESAFF_ERR_STATE, "no result");
+   return c->total_desc;
+}
+
+extern "C" int hesaff_result_keypoints(hesaff_ctx *c, hesaff_keypoint *out, size_t capacity)
+{
+   NEED_RESULT(c);
+   if ((size_t)c->total_desc > capacity) return fail(HESAFF_ERR_CAPACITY, "output capacity too small");
+   if (c->total_desc) CK(cudaMemcpy(out, c->d_keys, sizeof(hesaff_keypoint) * c->total_desc, cudaMemcpyDeviceToHost));
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_result_keypoints_device(hesaff_ctx *c, const hesaff_keypoint **out)
+{
+   NEED_RESULT(c);
+   *out = c->d_keys;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_result_ellipses(hesaff_ctx *c, float *out, size_t capacity)
+{
+   NEED_RESULT(c);
+   if ((size_t)c->total_desc > capacity) return fail(HESAFF_ERR_CAPACITY, "output capacity too small");
+   if (c->total_desc) CK(cudaMemcpy(out, c->d_ell, sizeof(float) * 5 * c->total_desc, cudaMemcpyDeviceToHost));
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_result_detections(hesaff_ctx *c, hesaff_detection *out, size_t capacity, int64_t *n_total)
+{
+   NEED_RESULT(c);
+   if (c->last_chunks != 1) return fail(HESAFF_ERR_STATE, "per-detection records are kept for single-chunk calls only");
+   if (n_total) *n_total = c->total_det;
+   if (!out) return HESAFF_OK;
+   if ((size_t)c->total_det > capacity) return fail(HESAFF_ERR_CAPACITY, "output capacity too small");
+   if ((size_t)c->total_det > c->dets_cap) {
+      if (c->d_dets) cudaFree(c->d_dets);
+      c->d_dets = nullptr;
+      int rc;
+      if ((rc = dmalloc(&c->d_dets, (size_t)c->total_det + 16))) return rc;
+      c->dets_cap = c->total_det + 16;
+   }
+   const size_t nwords = c->geom.mask_stride * c->n_images;
+   const uint32_t *d_count = c->woff + nwords;
+   ha_launch_scan_flags(c->cand.flags, HA_F_DET, d_count, c->cand_cap, c->det_off, c->scan_tmp, c->stream, c->lc);
+   ha_launch_export_detections(c->cand, d_count, c->cand_cap, c->det_off, c->d_geom, c->d_dets, c->stream, c->lc);
+   CK(cudaStreamSynchronize(c->stream));
+   if (c->total_det) CK(cudaMemcpy(out, c->d_dets, sizeof(hesaff_detection) * c->total_det, cudaMemcpyDeviceToHost));
+   return HESAFF_OK;
+}
+
+// ---- stage access -------------------------------------------------------------------------------------------
+extern "C" int hesaff_debug_geometry(hesaff_ctx *c, int *n_octaves, int *n_levels)
+{
+   NEED_RESULT(c);
+   if (n_octaves) *n_octaves = c->geom.nOct;
+   if (n_levels) *n_levels = c->geom.S + 2;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_debug_octave_size(hesaff_ctx *c, int octave, int *width, int *height)
+{
+   NEED_RESULT(c);
+   if (octave < 0 || octave >= c->geom.nOct) return fail(HESAFF_ERR_INVALID, "bad octave");
+   if (width) *width = c->geom.w[octave];
+   if (height) *height = c->geom.h[octave];
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_debug_plane(hesaff_ctx *c, int image, int octave, int level, int kind, float *out)
+{
+   NEED_RESULT(c);
+   if (c->last_chunks != 1) return fail(HESAFF_ERR_STATE, "planes are kept for single-chunk calls only");
+   const Geom &g = c->geom;
+   if (image < 0 || image >= c->n_images || octave < 0 || octave >= g.nOct || level < 0 || level >= g.S + 2)
+      return fail(HESAFF_ERR_INVALID, "bad plane index");
+   const float *p = c->arena + (size_t)image * g.arena_stride + (kind ? g.R_off[octave][level] : g.L_off[octave][level]);
+   CK(cudaMemcpy2D(out, sizeof(float) * g.w[octave], p, sizeof(float) * g.pitch[octave], sizeof(float) * g.w[octave],
+                   g.h[octave], cudaMemcpyDeviceToHost));
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, size_t capacity_patches)
+{
+   NEED_RESULT(c);
+   if (c->last_chunks != 1) return fail(HESAFF_ERR_STATE, "patches can be recomputed for single-chunk calls only");
+   if ((size_t)c->total_desc > capacity_patches) return fail(HESAFF_ERR_CAPACITY, "output capacity too small");
+   if (!c->total_desc) return HESAFF_OK;
+   float *d = nullptr;
+   int rc;
+   if ((rc = dmalloc(&d, (size_t)c->total_desc * HA_PATCH_PX))) return rc;
+   CK(cudaMemsetAsync(c->counters + 1, 0, sizeof(int) * 3, c->stream));
+   ha_launch_describe(c->arena, c->d_geom, c->tables, c->cand, c->bins, c->counters + 1, c->scratch, c->scratch_per_cta,
+                      c->large_ctas, c->maxP, d, normalized, c->desc_off, c->stream, c->lc);
+   CK(cudaStreamSynchronize(c->stream));
+   cudaError_t e = cudaMemcpy(out, d, sizeof(float) * HA_PATCH_PX * c->total_desc, cudaMemcpyDeviceToHost);
+   cudaFree(d);
+   CK(e);
+   return HESAFF_OK;
+}
+
+extern "C" int64_t hesaff_launch_count(hesaff_ctx *c, int reset)
+{
+   if (!c) return 0;
+   const int64_t v = c->lc.n;
+   if (reset) c->lc.n = 0;
+   return v;
+}
+
+extern "C" int hesaff_set_profiling(hesaff_ctx *c, int enable)
+{
+   if (!c) return fail(HESAFF_ERR_INVALID, "ctx is NULL");
+   c->profiling = enable != 0;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_stage_times_ms(hesaff_ctx *c, float *out6)
+{
+   if (!c || !out6) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   memcpy(out6, c->stage_ms, sizeof(c->stage_ms));
+   return HESAFF_OK;
+}
+
+// exportKeypoints, hesaff.cpp:107-130 (text formatting on the host; ostream defaults = 6 significant digits)
+extern "C" int hesaff_write_sift_file(const char *path, const hesaff_keypoint *kps, size_t n, float desc_factor)
+{
+   if (!path || (!kps && n)) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   std::ofstream out(path);
+   if (!out) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
+   out << 128 << std::endl;
+   out << n << std::endl;
+   for (size_t i = 0; i < n; i++) {
+      const hesaff_keypoint &k = kps[i];
+      const double sc = (double)(desc_factor * k.s);
+      const double a = k.a11, b = k.a12, c = k.a21, d = k.a22;
+      const double p = a * a + b * b, q = a * c + b * d, r = c * c + d * d;
+      const double det = p * r - q * q, isc2 = 1.0 / (sc * sc);
+      out << k.x << " " << k.y << " " << (float)(r / det * isc2) << " " << (float)(-q / det * isc2) << " "
+          << (float)(p / det * isc2);
+      for (size_t j = 0; j < 128; j++) out << " " << int(k.desc[j]);
+      out << std::endl;
+   }
+   return (int)n;
+}
