@@ -1,0 +1,141 @@
+// hesaff_b200/host/hesaff_main.cpp -- C++ host, drop-in for the reference CLI `hesaff <image>`
+// (hesaff.cpp:133-180): same HessianAffineParams, same stdout line, same <image>.hesaff.sift output format
+// (README:27-44), calling the sm_100a CUDA path through the C-ABI of include/hesaff_b200.h.
+//
+//   hesaff image.pgm|image.ppm [--threshold T] [--scales S] [--max-octaves K] [--device D] [image2 ...]
+//
+// No OpenCV: PNM (P5/P6, maxval 255) is read here; P6 is converted with the reference's expression
+// gray = (float(B) + G + R) / 3.0f (hesaff.cpp:144).  There is no CPU fallback: without a usable B200 the
+// program reports the library's error and exits non-zero.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+#include "../../include/hesaff_b200.h"
+
+using namespace std;
+
+// hesaff.cpp:21-36
+struct HessianAffineParams
+{
+   float threshold;
+   int   max_iter;
+   float desc_factor;
+   int   patch_size;
+   bool  verbose;
+   HessianAffineParams()
+      {
+         threshold = 16.0f/3.0f;
+         max_iter = 16;
+         desc_factor = 3.0f*sqrt(3.0f);
+         patch_size = 41;
+         verbose = false;
+      }
+};
+
+static double wallTime()
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double)ts.tv_sec + (double)ts.tv_nsec / 1.0e9;
+}
+
+// Reads P5/P6 with maxval 255. gray: h*w bytes when the file is P5; rgb non-empty when P6.
+static bool readPNM(const char *path, int &w, int &h, vector<unsigned char> &gray, vector<unsigned char> &rgb)
+{
+   ifstream f(path, ios::binary);
+   if (!f) return false;
+   string magic;
+   f >> magic;
+   if (magic != "P5" && magic != "P6") return false;
+   int vals[3], got = 0;
+   while (got < 3 && f) {
+      int ch = f.peek();
+      if (ch == '#') { string line; getline(f, line); continue; }
+      if (isspace(ch)) { f.get(); continue; }
+      f >> vals[got++];
+   }
+   f.get();
+   if (got < 3 || vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0) return false;
+   w = vals[0]; h = vals[1];
+   vector<unsigned char> &dst = (magic == "P5") ? gray : rgb;
+   dst.resize((size_t)w * h * (magic == "P5" ? 1 : 3));
+   f.read((char *)dst.data(), dst.size());
+   return (size_t)f.gcount() == dst.size();
+}
+
+int main(int argc, char **argv)
+{
+   HessianAffineParams par;
+   hesaff_params p;
+   hesaff_params_default(&p);
+   int device = 0;
+   vector<const char *> files;
+   for (int i = 1; i < argc; i++) {
+      if (!strcmp(argv[i], "--threshold") && i + 1 < argc) par.threshold = (float)atof(argv[++i]);
+      else if (!strcmp(argv[i], "--scales") && i + 1 < argc) p.number_of_scales = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "--max-octaves") && i + 1 < argc) p.max_octaves = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+      else files.push_back(argv[i]);
+   }
+   if (files.empty()) {
+      printf("\nUsage: hesaff image_name.ppm\nDetects Hessian Affine points and describes them using SIFT descriptor.\nThe detector assumes that the vertical orientation is preserved.\n\n");
+      return 0;
+   }
+   // copy params (hesaff.cpp:150-163)
+   p.threshold = par.threshold;
+   p.max_iter = par.max_iter;
+   p.patch_size = par.patch_size;
+   p.desc_factor = par.desc_factor;
+   p.verbose = par.verbose;
+
+   int status = 0;
+   for (size_t fi = 0; fi < files.size(); fi++) {
+      int w = 0, h = 0;
+      vector<unsigned char> gray, rgb;
+      vector<hesaff_keypoint> keys;
+      int nDetected = 0, nAffine = 0;
+      double t1 = 0, elapsed = 0;
+      if (readPNM(files[fi], w, h, gray, rgb)) {
+         hesaff_ctx *ctx = 0;
+         int rc = hesaff_create(&ctx, &p, device, w, h, 1, 0);
+         if (rc == HESAFF_OK) {
+            if (!rgb.empty()) {
+               vector<float> image((size_t)w * h);
+               const unsigned char *in = rgb.data();   // PNM is RGB; the sum is order independent
+               for (size_t i = 0; i < image.size(); i++, in += 3) image[i] = (float(in[0]) + in[1] + in[2]) / 3.0f;
+               t1 = wallTime();
+               rc = hesaff_detect_f32(ctx, image.data(), 1, w, h, sizeof(float) * w, sizeof(float) * w * h, 0, 0);
+            } else {
+               t1 = wallTime();
+               rc = hesaff_detect_u8(ctx, gray.data(), 1, w, h, (size_t)w, (size_t)w * h, 0, 0);
+            }
+            if (rc == HESAFF_OK) {
+               rc = hesaff_result_counts(ctx, &nDetected, &nAffine);
+               keys.resize((size_t)hesaff_result_total(ctx));
+               if (rc == HESAFF_OK && !keys.empty()) rc = hesaff_result_keypoints(ctx, keys.data(), keys.size());
+               elapsed = wallTime() - t1;
+            }
+         }
+         if (rc != HESAFF_OK) {
+            fprintf(stderr, "hesaff_b200: %s\n", hesaff_last_error());
+            if (ctx) hesaff_destroy(ctx);
+            return 2;
+         }
+         hesaff_destroy(ctx);
+      }
+      // an unreadable file behaves like the reference: empty image -> "128\n0\n", exit code 0
+      cout << "Detected " << nDetected << " keypoints and " << nAffine << " affine shapes in " << elapsed << " sec." << endl;
+      string out = string(files[fi]) + ".hesaff.sift";
+      if (hesaff_write_sift_file(out.c_str(), keys.data(), keys.size(), par.desc_factor) < 0) {
+         fprintf(stderr, "hesaff_b200: %s\n", hesaff_last_error());
+         status = 1;
+      }
+   }
+   return status;
+}

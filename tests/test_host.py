@@ -1,0 +1,117 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/hesaff_b200.h
+declares, the parameter block mirrors the reference structs, the sharding logic works over gloo (world 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    import hesaff_b200
+    hdr = open(os.path.join(ROOT, "include", "hesaff_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hesaff_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(hesaff_b200.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(hesaff_b200.EXPORTED_SYMBOLS) == declared
+    assert lib.hesaff_abi_version() == 1
+
+
+def test_params_default_mirror_reference_structs(port_oracle):
+    import hesaff_b200
+    p = hesaff_b200.HessianAffineParams()
+    o = port_oracle.default_params()
+    for name in ("threshold", "max_iter", "desc_factor", "patch_size", "number_of_scales", "initial_sigma",
+                 "edge_eigenvalue_ratio", "border", "convergence_threshold", "smm_window_size", "max_octaves"):
+        assert getattr(p, name) == getattr(o, name), name
+    assert ctypes.sizeof(hesaff_b200.HessianAffineParams) == 48
+    assert hesaff_b200.KEYPOINT_DTYPE.itemsize == 164      # struct Keypoint, hesaff.cpp:41-48
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the CPU."""
+    import torch
+    import hesaff_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hesaff_b200.HesaffError, match="no CUDA device|CUDA"):
+        hesaff_b200.AffineHessianDetector()
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may touch oracle/."""
+    pkg = os.path.join(ROOT, "hesaff_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "from oracle" not in src and "import oracle" not in src and "oracle_api.h" not in src, f
+                assert "libhesaff_oracle" not in src and "libhesaff_ref" not in src, f
+
+
+def test_sift_file_writer_format(tmp_path):
+    import hesaff_b200
+    k = np.zeros(2, hesaff_b200.KEYPOINT_DTYPE)
+    k["x"] = [12.5, 1234.5678]; k["y"] = [7.25, 0.001234567]; k["s"] = [2.0, 3.0]
+    k["a11"] = [1.0, 1.25]; k["a21"] = [0.0, 0.1]; k["a22"] = [1.0, 0.8]
+    k["desc"][0, :3] = [1, 2, 255]
+    path = str(tmp_path / "t.sift")
+    n = hesaff_b200.lib().hesaff_write_sift_file(path.encode(), k.ctypes.data, 2, ctypes.c_float(3.0 * np.sqrt(3.0)))
+    assert n == 2
+    lines = open(path).read().split("\n")
+    assert lines[0] == "128" and lines[1] == "2" and lines[4] == ""
+    t0 = lines[2].split()
+    assert len(t0) == 133 and t0[0] == "12.5" and t0[1] == "7.25" and t0[5:8] == ["1", "2", "255"]
+    assert lines[3].split()[0] == "1234.57" and lines[3].split()[1] == "0.00123457"   # ostream default: 6 significant digits
+    sc2 = (3.0 * np.sqrt(3.0) * 2.0) ** 2
+    assert abs(float(t0[2]) - 1.0 / sc2) < 1e-7 and float(t0[3]) == 0.0
+
+
+def test_partition_and_offsets():
+    from hesaff_b200 import shard
+    assert shard.partition(8192, 8).tolist() == [1024 * i for i in range(9)]
+    assert shard.partition(10, 4).tolist() == [0, 3, 6, 8, 10]
+    assert shard.partition(3, 8).tolist() == [0, 1, 2, 3, 3, 3, 3, 3, 3]
+    c = np.array([[5, 3], [9, 9], [0, 0], [4, 1]])
+    assert shard.global_offsets(c).tolist() == [0, 3, 12, 12, 13]
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hesaff_b200 import shard
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+n_total = 7
+starts = shard.partition(n_total, 2)
+rng = np.random.default_rng(0)
+all_counts = rng.integers(0, 1000, (n_total, 2)).astype(np.int32)
+mine = all_counts[starts[rank]:starts[rank + 1]]
+g = shard.all_gather_counts(dist, torch, mine, "cpu")
+assert g.shape == (n_total, 2) and np.array_equal(g, all_counts), (rank, g)
+off = shard.global_offsets(g)
+assert off[-1] == all_counts[:, 1].sum() and off[starts[1]] == all_counts[:starts[1], 1].sum()
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_count_all_gather_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
