@@ -285,44 +285,68 @@ struct NmsArgs {
    unsigned long long mask_stride;
 };
 
-__global__ void __launch_bounds__(256) k_nms(NmsArgs a)
+// Each warp owns a strip of 32 columns (= one mask word per row) and marches down NMS_ROWS rows keeping, per
+// response plane, the horizontal 3-max / 3-min of the two previous rows in registers: every response value is
+// loaded once per level (plus the 2 strip-edge columns), i.e. 3 x 4 B per pixel-level.
+#define NMS_ROWS 32
+#define NMS_WARPS 4
+
+__global__ void __launch_bounds__(NMS_WARPS * 32) k_nms(NmsArgs a)
 {
-   const int lane = threadIdx.x;
-   const int wcol = blockIdx.x;
-   const int r = blockIdx.y * blockDim.y + threadIdx.y;
-   if (r >= a.H) return;
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int wcol = blockIdx.x * NMS_WARPS + wid;
+   if (wcol >= a.wpr) return;
    const int c = wcol * 32 + lane;
+   const int cc = min(c, a.W - 1);                       // clamped column for the loads of out-of-image lanes
+   const int cl = max(cc - 1, 0), cr = min(cc + 1, a.W - 1);
+   const int r0 = blockIdx.y * NMS_ROWS;
+   const int r1 = min(r0 + NMS_ROWS, a.H);
    const size_t ioff = (size_t)blockIdx.z * a.img_stride;
-   bool cand = false;
-   if (r >= a.border && r < a.H - a.border && c >= a.border && c < a.W - a.border) {
-      const float *cur = a.cur + ioff + (size_t)r * a.pitch + c;
-      const float val = *cur;
-      if (val > a.posThr) {
-         const float *low = a.low + ioff + (size_t)r * a.pitch + c, *high = a.high + ioff + (size_t)r * a.pitch + c;
-         bool ok = true;
+   const float *planes[3] = {a.low + ioff, a.cur + ioff, a.high + ioff};
+   uint32_t *mrow = a.mask + (size_t)blockIdx.z * a.mask_stride + wcol;
+   const bool col_ok = c >= a.border && c < a.W - a.border;
+
+   float hmax[3][2], hmin[3][2], vcur[2];
 #pragma unroll
-         for (int dy = -1; dy <= 1; dy++)
+   for (int p = 0; p < 3; p++) { hmax[p][0] = hmax[p][1] = 0.f; hmin[p][0] = hmin[p][1] = 0.f; }
+   vcur[0] = vcur[1] = 0.f;
+
+   for (int rr = r0 - 1; rr <= r1; rr++) {
+      const int rl = min(max(rr, 0), a.H - 1);
+      float nmax[3], nmin[3], vnew = 0.f;
 #pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-               const int o = dy * a.pitch + dx;
-               ok = ok && !(cur[o] > val) && !(low[o] > val) && !(high[o] > val);
-            }
-         cand = ok;
-      } else if (val < a.negThr) {
-         const float *low = a.low + ioff + (size_t)r * a.pitch + c, *high = a.high + ioff + (size_t)r * a.pitch + c;
-         bool ok = true;
-#pragma unroll
-         for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-               const int o = dy * a.pitch + dx;
-               ok = ok && !(cur[o] < val) && !(low[o] < val) && !(high[o] < val);
-            }
-         cand = ok;
+      for (int p = 0; p < 3; p++) {
+         const float *row = planes[p] + (size_t)rl * a.pitch;
+         const float v = __ldg(row + cc);
+         float l = __shfl_up_sync(0xffffffffu, v, 1);
+         float r = __shfl_down_sync(0xffffffffu, v, 1);
+         if (lane == 0) l = __ldg(row + cl);
+         if (lane == 31) r = __ldg(row + cr);
+         nmax[p] = fmaxf(fmaxf(l, r), v);
+         nmin[p] = fminf(fminf(l, r), v);
+         if (p == 1) vnew = v;
       }
+      if (rr >= r0 + 1) {
+         const int ro = rr - 1;   // output row: rows ro-1 (age 0), ro (age 1), ro+1 (new) are available
+         float M = fmaxf(fmaxf(hmax[0][0], hmax[0][1]), nmax[0]);
+         float m = fminf(fminf(hmin[0][0], hmin[0][1]), nmin[0]);
+#pragma unroll
+         for (int p = 1; p < 3; p++) {
+            M = fmaxf(M, fmaxf(fmaxf(hmax[p][0], hmax[p][1]), nmax[p]));
+            m = fminf(m, fminf(fminf(hmin[p][0], hmin[p][1]), nmin[p]));
+         }
+         const float val = vcur[1];
+         // findLevelKeypoints (pyramid.cpp:215-217): val > positiveThreshold and no neighbour above it (ties pass),
+         // or val < negativeThreshold and no neighbour below it
+         const bool cand = col_ok && ro >= a.border && ro < a.H - a.border &&
+                           ((val > a.posThr && !(M > val)) || (val < a.negThr && !(m < val)));
+         const unsigned word = __ballot_sync(0xffffffffu, cand);
+         if (lane == 0) mrow[(size_t)ro * a.wpr] = word;
+      }
+#pragma unroll
+      for (int p = 0; p < 3; p++) { hmax[p][0] = hmax[p][1]; hmax[p][1] = nmax[p]; hmin[p][0] = hmin[p][1]; hmin[p][1] = nmin[p]; }
+      vcur[0] = vcur[1]; vcur[1] = vnew;
    }
-   const unsigned m = __ballot_sync(0xffffffffu, cand);
-   if (lane == 0) a.mask[(size_t)blockIdx.z * a.mask_stride + (size_t)r * a.wpr + wcol] = m;
 }
 
 void ha_launch_nms(const float *arena, const Geom &g, const Geom *, uint32_t *mask, int n, cudaStream_t st, LaunchCounter &lc)
@@ -335,8 +359,8 @@ void ha_launch_nms(const float *arena, const Geom &g, const Geom *, uint32_t *ma
          a.W = g.w[o]; a.H = g.h[o]; a.pitch = g.pitch[o]; a.border = g.border; a.wpr = g.wpr[o];
          a.posThr = g.positiveThreshold; a.negThr = g.negativeThreshold;
          a.mask = mask + g.mask_off[o][l]; a.mask_stride = g.mask_stride;
-         dim3 block(32, 8), grid(g.wpr[o], (g.h[o] + 7) / 8, n);
-         k_nms<<<grid, block, 0, st>>>(a);
+         dim3 grid((g.wpr[o] + NMS_WARPS - 1) / NMS_WARPS, (g.h[o] + NMS_ROWS - 1) / NMS_ROWS, n);
+         k_nms<<<grid, NMS_WARPS * 32, 0, st>>>(a);
          lc.n++;
       }
 }

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into small text files for profiles/.
+   python tools/ncu_summary.py launches <launches.csv>          -> per-kernel share table
+   python tools/ncu_summary.py raw <file.ncu-rep> [regex]        -> key raw metrics per captured launch"""
+import collections, csv, re, subprocess, sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) <= vi or "time_duration" not in r[hdr.index("Metric Name")]:
+            continue
+        name = re.sub(r"\(.*", "", r[ki])
+        v = float(r[vi].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(r[ui], v)
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print("kernel                                   launches     total_us   share")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-40s %8d %12.1f  %5.1f%%" % (k[:40], a[0], a[1], 100 * a[1] / tot))
+    print("%-40s %8d %12.1f" % ("TOTAL", sum(a[0] for a in agg.values()), tot))
+
+
+def raw(path, pat=None):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if pat and not re.search(pat, name):
+            continue
+        print("== %s  grid %s block %s" % (re.sub(r"\(.*", "", name), r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "?",
+                                          r[hdr.index("launch__block_size")] if "launch__block_size" in hdr else "?"))
+        for k in KEYS:
+            if k in hdr:
+                print("   %-85s %s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](*sys.argv[2:])
