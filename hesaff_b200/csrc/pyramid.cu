@@ -9,6 +9,7 @@
 //   HessianDetector::localizeKeypoint, solveLinear3x3        pyramid.cpp:122-204, helpers.cpp:46-88
 //   getHessianPointType                                      pyramid.cpp:24-37
 //   octaveMap dedup                                          pyramid.cpp:189-193,226
+#include <stdlib.h>
 #include "common.cuh"
 
 // =================================================================================================
@@ -226,6 +227,11 @@ int ha_launch_blur(const float *src, float *dstL, float *dstR, float *half, int 
                    int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
                    LaunchCounter &lc)
 {
+   static const bool use_tma = getenv("HESAFF_NO_TMA") == nullptr;
+   if (use_tma && ha_launch_blur_tma(src, dstL, dstR, half, W, H, pitch, hW, hH, hpitch, img_stride, norm, taps, n, st) == 0) {
+      lc.n++;
+      return 0;
+   }
    BlurArgs a;
    a.src = src; a.dstL = dstL; a.dstR = dstR; a.half = half; a.img_stride = img_stride;
    a.W = W; a.H = H; a.pitch = pitch; a.hW = hW; a.hH = hH; a.hpitch = hpitch;
