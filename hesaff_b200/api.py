@@ -27,7 +27,7 @@ HESSIAN_DARK, HESSIAN_BRIGHT, HESSIAN_SADDLE = 0, 1, 2   # pyramid.h:51-55
 EXPORTED_SYMBOLS = [
     "hesaff_abi_version", "hesaff_last_error", "hesaff_params_default", "hesaff_create", "hesaff_destroy",
     "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
-    "hesaff_result_keypoints_device", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
+    "hesaff_result_keypoints_device", "hesaff_set_host_output", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
     "hesaff_debug_octave_size", "hesaff_debug_plane", "hesaff_debug_patches", "hesaff_launch_count",
     "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_write_sift_file",
 ]
@@ -77,6 +77,7 @@ def lib():
         L.hesaff_result_total.restype = C.c_int64
         L.hesaff_result_keypoints.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.hesaff_result_keypoints_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.hesaff_set_host_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.hesaff_result_ellipses.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.hesaff_result_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.hesaff_debug_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -184,6 +185,14 @@ class AffineHessianDetector:
             out = np.empty(n, KEYPOINT_DTYPE)
         _check(lib().hesaff_result_keypoints(self._h, out.ctypes.data, len(out)))
         return out[:n]
+
+    def set_host_output(self, out):
+        """Stream every chunk's records into `out` (KEYPOINT_DTYPE array, ideally pinned) during detect; None disables."""
+        self._host_out = out
+        if out is None:
+            _check(lib().hesaff_set_host_output(self._h, None, 0))
+        else:
+            _check(lib().hesaff_set_host_output(self._h, out.ctypes.data, len(out)))
 
     def keys_device_ptr(self):
         p = C.c_void_p()

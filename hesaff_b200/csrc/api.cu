@@ -23,48 +23,65 @@ static int fail(int code, const std::string &msg)
          return fail(HESAFF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
    } while (0)
 
+// Per-chunk working set.  Two lanes (stream + buffers each) let the upload / pyramid / affine kernels of chunk k+1
+// run under the describe kernels of chunk k, and the D2H of finished records run under both.
+struct Lane {
+   cudaStream_t stream, aux;
+   cudaEvent_t ev_fork, ev_join;
+   float *arena;
+   uint8_t *stage_u8;
+   uint32_t *mask;
+   uint32_t *woff;             // scan of popc(mask): nwords+1
+   uint32_t *scan_tmp;
+   uint32_t *map;
+   Cand cand;
+   uint32_t *det_off, *desc_off;   // cand_cap+1 each
+   Bins bins;
+   int *counters;              // [0] affine work, [1..3] describe work
+   float *scratch;
+   cudaEvent_t ev[8];
+   cudaEvent_t done;           // recorded after the chunk's k_add_total
+   uint32_t *h_total;          // pinned: [0] described keypoints of the last chunk on this lane, [1] base offset
+   int pending_chunk;          // chunk index whose results are not yet copied to the host output (-1: none)
+};
+
 struct hesaff_ctx {
    hesaff_params par;
    int device;
    int max_w, max_h;
-   int chunk;                  // images resident at once
+   int chunk;                  // images resident at once per lane
+   int n_lanes;
    uint32_t cand_cap;          // candidate pool of one chunk
    int max_cand_per_image;
-   cudaStream_t stream;        // own stream
+   cudaStream_t stream;        // own stream (control / results)
+   cudaStream_t copy_stream;   // D2H of finished chunks
+   cudaEvent_t ev_start;
+   Lane lane[2];
    Geom geom;                  // host copy of the current geometry (W,H of the last call)
    Geom *d_geom;
    Taps taps0;                 // first blur (pyramid.cpp:278-279)
    Taps taps[HA_MAX_LVL];      // incremental blurs, level 1..S+1
    float norm[HA_MAX_LVL];     // sigma_l^2 passed to hessianResponse
    float lvl_sigma[HA_MAX_LVL];   // curSigma of each level (findLevelKeypoints(curSigma), pyramid.cpp:248)
-   // device memory
-   float *arena; size_t arena_bytes;
-   uint8_t *stage_u8; size_t stage_bytes;
-   uint32_t *mask; size_t mask_words_cap;
-   uint32_t *woff;             // scan of popc(mask): nwords+1
-   uint32_t *scan_tmp; size_t scan_tmp_elems;
-   uint32_t *map; size_t map_elems_cap;
-   Cand cand;
-   uint32_t *det_off, *desc_off;   // cand_cap+1 each
-   Bins bins;
-   int *counters;              // [0] affine work, [1..3] describe work, [4] overflow flag
-   float *scratch; size_t scratch_per_cta; int large_ctas; int maxP;
+   size_t mask_words_cap, map_elems_cap, scan_tmp_elems, stage_bytes;
+   size_t scratch_per_cta; int large_ctas; int maxP;
    Tables tables;
    std::vector<void *> table_allocs;
    // results of the last call
    int n_images;
    int *d_ndet, *d_ndesc; size_t counts_cap;
+   int *d_overflow;
    std::vector<int> h_ndet, h_ndesc;
    hesaff_keypoint *d_keys; float *d_ell; size_t keys_cap;
    uint32_t *d_out_base;       // running total of described keypoints over chunks
    hesaff_detection *d_dets; size_t dets_cap;
+   hesaff_keypoint *host_out; size_t host_out_cap; bool host_out_filled;   // optional streamed host output
    int64_t total_desc, total_det;
    int last_chunks;
    bool have_result;
    LaunchCounter lc;
-   // profiling
+   // profiling (forces single-lane, serialised execution so that stage times are clean)
    bool profiling;
-   cudaEvent_t ev[8];
    float stage_ms[6];
 };
 
@@ -260,6 +277,58 @@ template <typename T> static int dmalloc(T **p, size_t n)
    return HESAFF_OK;
 }
 
+static int alloc_lane(hesaff_ctx *c, Lane &L, const Geom &g)
+{
+   int rc;
+   memset(&L, 0, sizeof(L));
+   L.pending_chunk = -1;
+   CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+   CK(cudaStreamCreateWithFlags(&L.aux, cudaStreamNonBlocking));
+   CK(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming));
+   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&L.ev[i]));
+   CK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+   CK(cudaMallocHost((void **)&L.h_total, 4 * sizeof(uint32_t)));
+   const int chunk = c->chunk;
+   if ((rc = dmalloc(&L.arena, g.arena_stride * chunk))) return rc;
+   if ((rc = dmalloc(&L.stage_u8, c->stage_bytes))) return rc;
+   if ((rc = dmalloc(&L.mask, c->mask_words_cap + 1))) return rc;
+   if ((rc = dmalloc(&L.woff, c->mask_words_cap + 2))) return rc;
+   if ((rc = dmalloc(&L.scan_tmp, c->scan_tmp_elems))) return rc;
+   if ((rc = dmalloc(&L.map, c->map_elems_cap + 1))) return rc;
+   const size_t cc = c->cand_cap;
+   if ((rc = dmalloc(&L.cand.key, cc))) return rc;
+   if ((rc = dmalloc(&L.cand.x, cc)) || (rc = dmalloc(&L.cand.y, cc)) || (rc = dmalloc(&L.cand.s, cc)) ||
+       (rc = dmalloc(&L.cand.response, cc)) || (rc = dmalloc(&L.cand.cell, cc)) || (rc = dmalloc(&L.cand.type, cc)) ||
+       (rc = dmalloc(&L.cand.flags, cc)) || (rc = dmalloc(&L.cand.U, cc)) || (rc = dmalloc(&L.cand.A, cc)) ||
+       (rc = dmalloc(&L.cand.iters, cc)) || (rc = dmalloc(&L.cand.desc, cc * 128)))
+      return rc;
+   if ((rc = dmalloc(&L.det_off, cc + 2)) || (rc = dmalloc(&L.desc_off, cc + 2))) return rc;
+   for (int b = 0; b < 3; b++)
+      if ((rc = dmalloc(&L.bins.list[b], cc))) return rc;
+   if ((rc = dmalloc(&L.bins.count, 4))) return rc;
+   if ((rc = dmalloc(&L.counters, 8))) return rc;
+   if ((rc = dmalloc(&L.scratch, c->scratch_per_cta * c->large_ctas))) return rc;
+   return HESAFF_OK;
+}
+
+static void free_lane(Lane &L)
+{
+   if (L.stream) cudaStreamSynchronize(L.stream);
+   void *ptrs[] = {L.arena, L.stage_u8, L.mask, L.woff, L.scan_tmp, L.map, L.cand.key, L.cand.x, L.cand.y, L.cand.s,
+                   L.cand.response, L.cand.cell, L.cand.type, L.cand.flags, L.cand.U, L.cand.A, L.cand.iters, L.cand.desc,
+                   L.det_off, L.desc_off, L.bins.list[0], L.bins.list[1], L.bins.list[2], L.bins.count, L.counters, L.scratch};
+   for (void *p : ptrs) if (p) cudaFree(p);
+   for (int i = 0; i < 8; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
+   if (L.done) cudaEventDestroy(L.done);
+   if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+   if (L.ev_join) cudaEventDestroy(L.ev_join);
+   if (L.aux) cudaStreamDestroy(L.aux);
+   if (L.h_total) cudaFreeHost(L.h_total);
+   if (L.stream) cudaStreamDestroy(L.stream);
+   memset(&L, 0, sizeof(L));
+}
+
 extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int device, int max_width, int max_height,
                              int max_batch, int max_candidates_per_image)
 {
@@ -284,7 +353,10 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    c->par = *p; c->device = device; c->max_w = max_width; c->max_h = max_height;
    c->have_result = false; c->profiling = false; c->lc.n = 0;
    c->d_dets = nullptr; c->dets_cap = 0; c->d_keys = nullptr; c->d_ell = nullptr; c->keys_cap = 0;
-   c->d_ndet = c->d_ndesc = nullptr; c->counts_cap = 0;
+   c->d_ndet = c->d_ndesc = nullptr; c->counts_cap = 0; c->d_overflow = nullptr; c->d_out_base = nullptr; c->d_geom = nullptr;
+   c->host_out = nullptr; c->host_out_cap = 0; c->host_out_filled = false;
+   c->stream = c->copy_stream = nullptr; c->ev_start = nullptr; c->n_lanes = 0;
+   memset(c->lane, 0, sizeof(c->lane));
    memset(c->stage_ms, 0, sizeof(c->stage_ms));
    *out = c;   // so that a failed create can still be destroyed
 
@@ -317,46 +389,33 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    size_t free_b = 0, total_b = 0;
    CK(cudaMemGetInfo(&free_b, &total_b));
    const size_t pib = per_image_bytes(g, c->max_cand_per_image);
+   // two lanes of `chunk` images each; a batch that fits one chunk (max_batch given and small) still gets 2 lanes of
+   // that size so that consecutive calls need no reallocation
    int chunk = max_batch;
-   if (chunk <= 0) chunk = (int)std::min<size_t>(64, std::max<size_t>(1, (size_t)(free_b * 0.5) / pib));
-   if ((size_t)chunk * pib > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");
+   if (chunk <= 0) chunk = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)(free_b * 0.45) / (2 * pib)));
+   c->n_lanes = 2;
+   if ((size_t)chunk * pib * 2 > free_b * 0.85) c->n_lanes = 1;
+   if ((size_t)chunk * pib * c->n_lanes > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");
    c->chunk = chunk;
    if ((size_t)chunk * c->max_cand_per_image >= 0xFFFFFFF0ull) return fail(HESAFF_ERR_INVALID, "candidate pool exceeds 32-bit indexing");
    c->cand_cap = (uint32_t)((size_t)chunk * c->max_cand_per_image);
 
    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->ev[i]));
+   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+   CK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
    int rc;
    if ((rc = build_tables(c))) return rc;
    if ((rc = dmalloc(&c->d_geom, 1))) return rc;
-   c->arena_bytes = g.arena_stride * 4 * chunk;
-   if ((rc = dmalloc(&c->arena, g.arena_stride * chunk))) return rc;
+   if ((rc = dmalloc(&c->d_out_base, 2)) || (rc = dmalloc(&c->d_overflow, 2))) return rc;
    c->stage_bytes = (size_t)max_width * max_height * 4 * chunk;   // u8 or f32 host input staging
-   if ((rc = dmalloc(&c->stage_u8, c->stage_bytes))) return rc;
    c->mask_words_cap = g.mask_stride * chunk;
-   if ((rc = dmalloc(&c->mask, c->mask_words_cap + 1))) return rc;
-   if ((rc = dmalloc(&c->woff, c->mask_words_cap + 2))) return rc;
    c->scan_tmp_elems = std::max(ha_scan_tmp_elems(c->mask_words_cap), ha_scan_tmp_elems(c->cand_cap)) + 8;
-   if ((rc = dmalloc(&c->scan_tmp, c->scan_tmp_elems))) return rc;
    c->map_elems_cap = g.map_stride * chunk;
-   if ((rc = dmalloc(&c->map, c->map_elems_cap + 1))) return rc;
-   const size_t cc = c->cand_cap;
-   if ((rc = dmalloc(&c->cand.key, cc))) return rc;
-   if ((rc = dmalloc(&c->cand.x, cc)) || (rc = dmalloc(&c->cand.y, cc)) || (rc = dmalloc(&c->cand.s, cc)) ||
-       (rc = dmalloc(&c->cand.response, cc)) || (rc = dmalloc(&c->cand.cell, cc)) || (rc = dmalloc(&c->cand.type, cc)) ||
-       (rc = dmalloc(&c->cand.flags, cc)) || (rc = dmalloc(&c->cand.U, cc)) || (rc = dmalloc(&c->cand.A, cc)) ||
-       (rc = dmalloc(&c->cand.iters, cc)) || (rc = dmalloc(&c->cand.desc, cc * 128)))
-      return rc;
-   if ((rc = dmalloc(&c->det_off, cc + 2)) || (rc = dmalloc(&c->desc_off, cc + 2))) return rc;
-   for (int b = 0; b < 3; b++)
-      if ((rc = dmalloc(&c->bins.list[b], cc))) return rc;
-   if ((rc = dmalloc(&c->bins.count, 4))) return rc;
-   if ((rc = dmalloc(&c->counters, 8))) return rc;
-   if ((rc = dmalloc(&c->d_out_base, 2))) return rc;
    c->maxP = std::min(max_width, max_height) + 8;
    c->large_ctas = 148 * 2;
    c->scratch_per_cta = align_up((size_t)c->maxP * 82, 64);
-   if ((rc = dmalloc(&c->scratch, c->scratch_per_cta * c->large_ctas))) return rc;
+   for (int l = 0; l < c->n_lanes; l++)
+      if ((rc = alloc_lane(c, c->lane[l], g))) return rc;
    return HESAFF_OK;
 }
 
@@ -365,21 +424,48 @@ extern "C" int hesaff_destroy(hesaff_ctx *c)
    if (!c) return HESAFF_OK;
    cudaSetDevice(c->device);
    if (c->stream) cudaStreamSynchronize(c->stream);
-   void *ptrs[] = {c->d_geom, c->arena, c->stage_u8, c->mask, c->woff, c->scan_tmp, c->map, c->cand.key, c->cand.x,
-                   c->cand.y, c->cand.s, c->cand.response, c->cand.cell, c->cand.type, c->cand.flags, c->cand.U,
-                   c->cand.A, c->cand.iters, c->cand.desc, c->det_off, c->desc_off, c->bins.list[0], c->bins.list[1],
-                   c->bins.list[2], c->bins.count, c->counters, c->d_out_base, c->scratch, c->d_ndet, c->d_ndesc,
-                   c->d_keys, c->d_ell, c->d_dets};
+   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+   for (int l = 0; l < 2; l++) free_lane(c->lane[l]);
+   void *ptrs[] = {c->d_geom, c->d_out_base, c->d_overflow, c->d_ndet, c->d_ndesc, c->d_keys, c->d_ell, c->d_dets};
    for (void *p : ptrs) if (p) cudaFree(p);
    for (void *p : c->table_allocs) cudaFree(p);
-   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+   if (c->ev_start) cudaEventDestroy(c->ev_start);
    if (c->stream) cudaStreamDestroy(c->stream);
+   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
    delete c;
    return HESAFF_OK;
 }
 
+// Streamed host output: when set (pinned memory recommended), every chunk's Keypoint records are copied to
+// `out` as soon as the chunk is finished, overlapping the next chunks; hesaff_result_keypoints on the same pointer is
+// then free.  NULL disables.
+extern "C" int hesaff_set_host_output(hesaff_ctx *c, hesaff_keypoint *out, size_t capacity)
+{
+   if (!c) return fail(HESAFF_ERR_INVALID, "ctx is NULL");
+   c->host_out = out; c->host_out_cap = out ? capacity : 0; c->host_out_filled = false;
+   return HESAFF_OK;
+}
+
 // ---- the hot path ------------------------------------------------------------------------------------
-__global__ void k_add_total(uint32_t *base, const uint32_t *add) { *base += *add; }
+__global__ void k_add_total(uint32_t *base, const uint32_t *add, uint32_t *report)
+{
+   report[1] = *base;     // base offset of this chunk's records
+   report[0] = *add;      // number of records of this chunk
+   *base += *add;
+}
+
+// copies the records of the chunk that last ran on lane L to the streamed host output (if any)
+static int flush_lane_output(hesaff_ctx *c, Lane &L)
+{
+   if (L.pending_chunk < 0) return HESAFF_OK;
+   L.pending_chunk = -1;
+   CK(cudaEventSynchronize(L.done));
+   if (!c->host_out) return HESAFF_OK;
+   const size_t cnt = L.h_total[0], base = L.h_total[1];
+   if (base + cnt > c->host_out_cap) return fail(HESAFF_ERR_CAPACITY, "streamed host output buffer too small");
+   if (cnt) CK(cudaMemcpyAsync(c->host_out + base, c->d_keys + base, cnt * sizeof(hesaff_keypoint), cudaMemcpyDeviceToHost, c->copy_stream));
+   return HESAFF_OK;
+}
 
 static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int W, int H, size_t row_pitch,
                        size_t img_stride, int on_device, void *stream_)
@@ -391,13 +477,14 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
    if (row_pitch < (size_t)W * esz || img_stride < row_pitch * (size_t)(H - 1) + (size_t)W * esz)
       return fail(HESAFF_ERR_INVALID, "row pitch / image stride too small");
    CK(cudaSetDevice(c->device));
-   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : c->stream;
+   cudaStream_t ust = stream_ ? (cudaStream_t)stream_ : c->stream;
    c->have_result = false;
+   c->host_out_filled = false;
 
    Geom &g = c->geom;
    plan_geometry(c->par, W, H, g);
    for (int l = 0; l < g.S + 2; l++) g.sigma[l] = c->lvl_sigma[l];
-   CK(cudaMemcpyAsync(c->d_geom, &g, sizeof(Geom), cudaMemcpyHostToDevice, st));
+   CK(cudaMemcpyAsync(c->d_geom, &g, sizeof(Geom), cudaMemcpyHostToDevice, ust));
 
    // output buffers for the whole batch
    if ((size_t)n > c->counts_cap || !c->d_ndet) {
@@ -417,19 +504,31 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
       if ((rc = dmalloc(&c->d_keys, want_keys)) || (rc = dmalloc(&c->d_ell, want_keys * 5))) return rc;
       c->keys_cap = want_keys;
    }
-   CK(cudaMemsetAsync(c->d_ndet, 0, sizeof(int) * ((size_t)n + 1), st));
-   CK(cudaMemsetAsync(c->d_ndesc, 0, sizeof(int) * ((size_t)n + 1), st));
-   CK(cudaMemsetAsync(c->d_out_base, 0, sizeof(uint32_t) * 2, st));
-   CK(cudaMemsetAsync(c->counters + 4, 0, sizeof(int), st));
+   CK(cudaMemsetAsync(c->d_ndet, 0, sizeof(int) * ((size_t)n + 1), ust));
+   CK(cudaMemsetAsync(c->d_ndesc, 0, sizeof(int) * ((size_t)n + 1), ust));
+   CK(cudaMemsetAsync(c->d_out_base, 0, sizeof(uint32_t) * 2, ust));
+   CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int) * 2, ust));
+   CK(cudaEventRecord(c->ev_start, ust));
    memset(c->stage_ms, 0, sizeof(c->stage_ms));
    c->n_images = n;
    c->last_chunks = 0;
    const int S = g.S;
+   const int lanes = c->profiling ? 1 : c->n_lanes;
+   for (int l = 0; l < c->n_lanes; l++) {
+      c->lane[l].pending_chunk = -1;
+      CK(cudaStreamWaitEvent(c->lane[l].stream, c->ev_start, 0));
+   }
+   cudaEvent_t prev_done = nullptr;
 
-   for (int start = 0; start < n; start += c->chunk) {
+   for (int start = 0, k = 0; start < n; start += c->chunk, k++) {
       const int cn = std::min(c->chunk, n - start);
+      Lane &L = c->lane[k % lanes];
+      cudaStream_t st = L.stream;
+      // the lane's previous chunk must be finished before its buffers are reused by the host-side staging copy and
+      // before its records can be streamed out
+      { int rc = flush_lane_output(c, L); if (rc) return rc; }
       c->last_chunks++;
-      if (c->profiling) cudaEventRecord(c->ev[0], st);
+      if (c->profiling) cudaEventRecord(L.ev[0], st);
       // ---- stage 0: upload + gray float image (hesaff.cpp:138-148) ---------------------------------
       const char *src = (const char *)images + (size_t)start * img_stride;
       const void *dsrc = src;
@@ -437,21 +536,21 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
       if (!on_device) {
          d_row_pitch = (size_t)W * esz; d_img_stride = d_row_pitch * H;
          if (row_pitch == d_row_pitch && img_stride == d_img_stride)
-            CK(cudaMemcpyAsync(c->stage_u8, src, d_img_stride * cn, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(L.stage_u8, src, d_img_stride * cn, cudaMemcpyHostToDevice, st));
          else
             for (int i = 0; i < cn; i++)
-               CK(cudaMemcpy2DAsync(c->stage_u8 + (size_t)i * d_img_stride, d_row_pitch, src + (size_t)i * img_stride,
+               CK(cudaMemcpy2DAsync(L.stage_u8 + (size_t)i * d_img_stride, d_row_pitch, src + (size_t)i * img_stride,
                                     row_pitch, d_row_pitch, H, cudaMemcpyHostToDevice, st));
-         dsrc = c->stage_u8;
+         dsrc = L.stage_u8;
       }
-      float *img_plane = c->arena + g.img_off;
+      float *img_plane = L.arena + g.img_off;
       if (is_u8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
-      if (c->profiling) cudaEventRecord(c->ev[1], st);
+      if (c->profiling) cudaEventRecord(L.ev[1], st);
 
       // ---- stage 1: pyramid (pyramid.cpp:261-292, 224-259) ------------------------------------------
       if (g.nOct > 0) {
-         float *L00 = c->arena + g.L_off[0][0], *R00 = c->arena + g.R_off[0][0];
+         float *L00 = L.arena + g.L_off[0][0], *R00 = L.arena + g.R_off[0][0];
          if (c->taps0.n > 0) {
             if (ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0],
                                c->taps0, cn, st, c->lc))
@@ -464,69 +563,78 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
       }
       for (int o = 0; o < g.nOct; o++) {
          if (o > 0)   // response of the decimated first level (cur = hessianResponse(blur, sigma0^2), pyramid.cpp:230)
-            ha_launch_hessian(c->arena + g.L_off[o][0], c->arena + g.R_off[o][0], g.w[o], g.h[o], g.pitch[o], g.arena_stride,
+            ha_launch_hessian(L.arena + g.L_off[o][0], L.arena + g.R_off[o][0], g.w[o], g.h[o], g.pitch[o], g.arena_stride,
                               c->norm[0], cn, st, c->lc);
          for (int i = 1; i < S + 2; i++) {
             const bool seed_next = (i == S) && (o + 1 < g.nOct);   // halfImage(nextBlur) at i == numberOfScales
-            float *half = seed_next ? c->arena + g.L_off[o + 1][0] : nullptr;
-            if (ha_launch_blur(c->arena + g.L_off[o][i - 1], c->arena + g.L_off[o][i], c->arena + g.R_off[o][i], half, g.w[o],
+            float *half = seed_next ? L.arena + g.L_off[o + 1][0] : nullptr;
+            if (ha_launch_blur(L.arena + g.L_off[o][i - 1], L.arena + g.L_off[o][i], L.arena + g.R_off[o][i], half, g.w[o],
                                g.h[o], g.pitch[o], seed_next ? g.w[o + 1] : 0, seed_next ? g.h[o + 1] : 0,
                                seed_next ? g.pitch[o + 1] : 0, g.arena_stride, c->norm[i], c->taps[i], cn, st, c->lc))
                return fail(HESAFF_ERR_INVALID, "unsupported blur size");
          }
       }
-      if (c->profiling) cudaEventRecord(c->ev[2], st);
+      if (c->profiling) cudaEventRecord(L.ev[2], st);
 
       // ---- stage 2: extrema, ordered compaction, localisation, dedup ------------------------------------
       const size_t nwords = g.mask_stride * cn;
-      ha_launch_nms(c->arena, g, c->d_geom, c->mask, cn, st, c->lc);
-      ha_launch_scan_popc(c->mask, nwords, c->woff, c->scan_tmp, st, c->lc);
-      const uint32_t *d_count = c->woff + nwords;   // number of candidates in this chunk
-      ha_launch_expand(c->mask, c->woff, c->d_geom, nwords, c->cand, c->cand_cap, c->counters + 4, st, c->lc);
-      CK(cudaMemsetAsync(c->map, 0xFF, sizeof(uint32_t) * g.map_stride * cn, st));
-      ha_launch_localize(c->arena, c->d_geom, c->cand, d_count, c->cand_cap, c->map, st, c->lc);
-      if (c->profiling) cudaEventRecord(c->ev[3], st);
+      ha_launch_nms(L.arena, g, c->d_geom, L.mask, cn, st, c->lc);
+      ha_launch_scan_popc(L.mask, nwords, L.woff, L.scan_tmp, st, c->lc);
+      const uint32_t *d_count = L.woff + nwords;   // number of candidates in this chunk
+      ha_launch_expand(L.mask, L.woff, c->d_geom, nwords, L.cand, c->cand_cap, c->d_overflow, st, c->lc);
+      CK(cudaMemsetAsync(L.map, 0xFF, sizeof(uint32_t) * g.map_stride * cn, st));
+      ha_launch_localize(L.arena, c->d_geom, L.cand, d_count, c->cand_cap, L.map, st, c->lc);
+      if (c->profiling) cudaEventRecord(L.ev[3], st);
 
       // ---- stage 3: affine shape ---------------------------------------------------------------------
-      CK(cudaMemsetAsync(c->counters, 0, sizeof(int) * 4, st));
-      CK(cudaMemsetAsync(c->bins.count, 0, sizeof(int) * 4, st));
-      ha_launch_affine(c->arena, c->d_geom, c->tables, c->cand, d_count, c->cand_cap, c->map, c->d_ndet + start, c->bins,
-                       c->counters, st, c->lc);
-      if (c->profiling) cudaEventRecord(c->ev[4], st);
+      CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 4, st));
+      CK(cudaMemsetAsync(L.bins.count, 0, sizeof(int) * 4, st));
+      ha_launch_affine(L.arena, c->d_geom, c->tables, L.cand, d_count, c->cand_cap, L.map, c->d_ndet + start, L.bins,
+                       L.counters, st, c->lc);
+      if (c->profiling) cudaEventRecord(L.ev[4], st);
 
       // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
-      ha_launch_describe(c->arena, c->d_geom, c->tables, c->cand, c->bins, c->counters + 1, c->scratch, c->scratch_per_cta,
-                         c->large_ctas, c->maxP, nullptr, 0, nullptr, st, c->lc);
-      if (c->profiling) cudaEventRecord(c->ev[5], st);
+      ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
+                         c->large_ctas, c->maxP, nullptr, 0, nullptr, st, c->lc, L.aux, L.ev_fork, L.ev_join);
+      if (c->profiling) cudaEventRecord(L.ev[5], st);
 
       // ---- stage 5: ordered compaction into Keypoint records -------------------------------------------
-      ha_launch_scan_flags(c->cand.flags, HA_F_DESC, d_count, c->cand_cap, c->desc_off, c->scan_tmp, st, c->lc);
-      // records of this chunk start at the running total of the previous chunks (device-side base)
-      ha_launch_compact(c->cand, d_count, c->cand_cap, c->desc_off, c->d_geom, c->d_keys, c->d_ell, c->d_ndesc + start,
-                        c->d_out_base, (uint32_t)std::min<size_t>(c->keys_cap, 0xFFFFFFFFu), c->counters + 4, st, c->lc);
-      k_add_total<<<1, 1, 0, st>>>(c->d_out_base, c->desc_off + c->cand_cap);
+      ha_launch_scan_flags(L.cand.flags, HA_F_DESC, d_count, c->cand_cap, L.desc_off, L.scan_tmp, st, c->lc);
+      // records of this chunk start at the running total of the previous chunks (device-side base): chunk order
+      if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
+      ha_launch_compact(L.cand, d_count, c->cand_cap, L.desc_off, c->d_geom, c->d_keys, c->d_ell, c->d_ndesc + start,
+                        c->d_out_base, (uint32_t)std::min<size_t>(c->keys_cap, 0xFFFFFFFFu), c->d_overflow, st, c->lc);
+      uint32_t *d_report = nullptr;
+      CK(cudaHostGetDevicePointer((void **)&d_report, L.h_total, 0));
+      k_add_total<<<1, 1, 0, st>>>(c->d_out_base, L.desc_off + c->cand_cap, d_report);
       c->lc.n++;
+      CK(cudaEventRecord(L.done, st));
+      prev_done = L.done;
+      L.pending_chunk = k;
       if (c->profiling) {
-         cudaEventRecord(c->ev[6], st);
-         CK(cudaEventSynchronize(c->ev[6]));
-         for (int k = 0; k < 6; k++) {
+         cudaEventRecord(L.ev[6], st);
+         CK(cudaEventSynchronize(L.ev[6]));
+         for (int q = 0; q < 6; q++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]);
-            c->stage_ms[k] += ms;
+            cudaEventElapsedTime(&ms, L.ev[q], L.ev[q + 1]);
+            c->stage_ms[q] += ms;
          }
       }
    }
-   // counts to the host; this is the only synchronisation point of a single-chunk call
+   // drain: stream out the last chunks, then counts to the host
+   for (int l = 0; l < c->n_lanes; l++) { int rc = flush_lane_output(c, c->lane[l]); if (rc) return rc; }
+   for (int l = 0; l < c->n_lanes; l++) CK(cudaStreamSynchronize(c->lane[l].stream));
    c->h_ndet.assign(n, 0); c->h_ndesc.assign(n, 0);
    int overflow = 0;
    uint32_t total = 0;
    if (n > 0) {
-      CK(cudaMemcpyAsync(c->h_ndet.data(), c->d_ndet, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(c->h_ndesc.data(), c->d_ndesc, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(c->h_ndet.data(), c->d_ndet, sizeof(int) * n, cudaMemcpyDeviceToHost, ust));
+      CK(cudaMemcpyAsync(c->h_ndesc.data(), c->d_ndesc, sizeof(int) * n, cudaMemcpyDeviceToHost, ust));
    }
-   CK(cudaMemcpyAsync(&overflow, c->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
-   CK(cudaMemcpyAsync(&total, c->d_out_base, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-   CK(cudaStreamSynchronize(st));
+   CK(cudaMemcpyAsync(&overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ust));
+   CK(cudaMemcpyAsync(&total, c->d_out_base, sizeof(uint32_t), cudaMemcpyDeviceToHost, ust));
+   CK(cudaStreamSynchronize(ust));
+   CK(cudaStreamSynchronize(c->copy_stream));
    CK(cudaGetLastError());
    if (overflow) return fail(HESAFF_ERR_CAPACITY, "candidate pool / keypoint buffer overflow; raise max_candidates_per_image");
    if (total > c->keys_cap) return fail(HESAFF_ERR_CAPACITY, "keypoint output buffer overflow; raise max_candidates_per_image");
@@ -534,6 +642,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
    c->total_det = 0;
    for (int i = 0; i < n; i++) c->total_det += c->h_ndet[i];
    c->have_result = true;
+   c->host_out_filled = c->host_out != nullptr;
    return HESAFF_OK;
 }
 
@@ -575,6 +684,7 @@ extern "C" int hesaff_result_keypoints(hesaff_ctx *c, hesaff_keypoint *out, size
 {
    NEED_RESULT(c);
    if ((size_t)c->total_desc > capacity) return fail(HESAFF_ERR_CAPACITY, "output capacity too small");
+   if (out == c->host_out && c->host_out_filled) return HESAFF_OK;   // already streamed during the detect call
    if (c->total_desc) CK(cudaMemcpy(out, c->d_keys, sizeof(hesaff_keypoint) * c->total_desc, cudaMemcpyDeviceToHost));
    return HESAFF_OK;
 }
@@ -608,11 +718,12 @@ extern "C" int hesaff_result_detections(hesaff_ctx *c, hesaff_detection *out, si
       if ((rc = dmalloc(&c->d_dets, (size_t)c->total_det + 16))) return rc;
       c->dets_cap = c->total_det + 16;
    }
+   Lane &L = c->lane[0];
    const size_t nwords = c->geom.mask_stride * c->n_images;
-   const uint32_t *d_count = c->woff + nwords;
-   ha_launch_scan_flags(c->cand.flags, HA_F_DET, d_count, c->cand_cap, c->det_off, c->scan_tmp, c->stream, c->lc);
-   ha_launch_export_detections(c->cand, d_count, c->cand_cap, c->det_off, c->d_geom, c->d_dets, c->stream, c->lc);
-   CK(cudaStreamSynchronize(c->stream));
+   const uint32_t *d_count = L.woff + nwords;
+   ha_launch_scan_flags(L.cand.flags, HA_F_DET, d_count, c->cand_cap, L.det_off, L.scan_tmp, L.stream, c->lc);
+   ha_launch_export_detections(L.cand, d_count, c->cand_cap, L.det_off, c->d_geom, c->d_dets, L.stream, c->lc);
+   CK(cudaStreamSynchronize(L.stream));
    if (c->total_det) CK(cudaMemcpy(out, c->d_dets, sizeof(hesaff_detection) * c->total_det, cudaMemcpyDeviceToHost));
    return HESAFF_OK;
 }
@@ -642,7 +753,7 @@ extern "C" int hesaff_debug_plane(hesaff_ctx *c, int image, int octave, int leve
    const Geom &g = c->geom;
    if (image < 0 || image >= c->n_images || octave < 0 || octave >= g.nOct || level < 0 || level >= g.S + 2)
       return fail(HESAFF_ERR_INVALID, "bad plane index");
-   const float *p = c->arena + (size_t)image * g.arena_stride + (kind ? g.R_off[octave][level] : g.L_off[octave][level]);
+   const float *p = c->lane[0].arena + (size_t)image * g.arena_stride + (kind ? g.R_off[octave][level] : g.L_off[octave][level]);
    CK(cudaMemcpy2D(out, sizeof(float) * g.w[octave], p, sizeof(float) * g.pitch[octave], sizeof(float) * g.w[octave],
                    g.h[octave], cudaMemcpyDeviceToHost));
    return HESAFF_OK;
@@ -657,10 +768,11 @@ extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, s
    float *d = nullptr;
    int rc;
    if ((rc = dmalloc(&d, (size_t)c->total_desc * HA_PATCH_PX))) return rc;
-   CK(cudaMemsetAsync(c->counters + 1, 0, sizeof(int) * 3, c->stream));
-   ha_launch_describe(c->arena, c->d_geom, c->tables, c->cand, c->bins, c->counters + 1, c->scratch, c->scratch_per_cta,
-                      c->large_ctas, c->maxP, d, normalized, c->desc_off, c->stream, c->lc);
-   CK(cudaStreamSynchronize(c->stream));
+   Lane &L = c->lane[0];
+   CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 3, L.stream));
+   ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
+                      c->large_ctas, c->maxP, d, normalized, L.desc_off, L.stream, c->lc);
+   CK(cudaStreamSynchronize(L.stream));
    cudaError_t e = cudaMemcpy(out, d, sizeof(float) * HA_PATCH_PX * c->total_desc, cudaMemcpyDeviceToHost);
    cudaFree(d);
    CK(e);

@@ -6,8 +6,8 @@
 // OpenCV's): row pass = left-to-right FMA chain stored as fp32, column pass = centre*k0 then (above+below) FMA'd
 // outwards; the packed instructions round each lane separately (bit-identical results).
 //
-// Tile: 128 x 60 outputs per CTA (+1 px ring for the Hessian), 256 threads.
-//   1. one thread arms an mbarrier and issues ONE 3-D TMA box load {x, y, image} of (132+2R) x (64+2R) floats;
+// Tile: 128 x 54 outputs per CTA (+1 px ring for the Hessian), 320 threads, up to 3 CTAs per SM.
+//   1. one thread arms an mbarrier and issues ONE 3-D TMA box load {x, y, image} of (~132+2R) x (56+2R) floats;
 //      out-of-image elements arrive as zeros;
 //   2. CTAs that touch the image border rewrite those elements with the clamped (BORDER_REPLICATE) value;
 //   3. row pass, 4 outputs / thread from LDS.128 loads; 4. column pass, 2 columns x 4 rows / thread on f32x2;
@@ -16,9 +16,9 @@
 #include "common.cuh"
 
 namespace blur2 {
-constexpr int TW = 128, TH = 60;          // outputs written per tile
-constexpr int OH = 64;                    // output rows computed per tile (ring + padding to x4)
-constexpr int THREADS = 256;
+constexpr int TW = 128, TH = 54;          // outputs written per tile
+constexpr int OH = 56;                    // output rows computed per tile (TH + ring, multiple of 4)
+constexpr int THREADS = 320;
 constexpr int MAXN = 21;
 // TMA needs the box's first column 16-byte aligned: the box starts PADL = roundup(R+1, 4) columns left of the
 // tile, so the computed output columns start PADO = PADL - R (1..4) columns left of it (>= the 1-px Hessian ring).

@@ -153,7 +153,8 @@ void ha_launch_affine(const float *arena, const Geom *dg, Tables tb, Cand cand, 
                       const uint32_t *map, int *n_det, Bins bins, int *work_counter, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_describe(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,
                         float *scratch, size_t scratch_per_cta, int large_ctas, int maxP, float *patch_dump,
-                        int dump_normalized, const uint32_t *dump_index, cudaStream_t st, LaunchCounter &lc);
+                        int dump_normalized, const uint32_t *dump_index, cudaStream_t st, LaunchCounter &lc,
+                        cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 void ha_launch_compact(Cand cand, const uint32_t *count, uint32_t cap, const uint32_t *desc_off, const Geom *dg,
                        hesaff_keypoint *out, float *ellipses, int *n_desc, const uint32_t *out_base, uint32_t keys_cap,
                        int *overflow, cudaStream_t st, LaunchCounter &lc);

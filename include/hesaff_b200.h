@@ -119,6 +119,10 @@ int64_t hesaff_result_total(hesaff_ctx *ctx);
  * level, row, column of the initial extremum: the order keys.push_back sees).  Image i's records start
  * at the exclusive prefix sum of n_described.  capacity in records; HESAFF_ERR_CAPACITY if too small. */
 int hesaff_result_keypoints(hesaff_ctx *ctx, hesaff_keypoint *out, size_t capacity);
+/* Optional streamed output: when `out` is set (pinned host memory makes it asynchronous), every chunk's records are
+ * copied to out[...] as soon as the chunk is finished, overlapping the work of the following chunks; a later
+ * hesaff_result_keypoints(ctx, out, ...) on the same pointer then costs nothing.  NULL disables. */
+int hesaff_set_host_output(hesaff_ctx *ctx, hesaff_keypoint *out, size_t capacity);
 /* Same records, device pointer (valid until the next detect call). */
 int hesaff_result_keypoints_device(hesaff_ctx *ctx, const hesaff_keypoint **out);
 /* exportKeypoints maths (hesaff.cpp:115-125): per keypoint (u, v, a, b, c) with
