@@ -141,6 +141,20 @@ def _cpu_worker(args):
     return time.perf_counter() - t, int(len(d)), int(d["described"].sum())
 
 
+def physical_cores():
+    """Worker count for the CPU reference: one process per physical core (SMT siblings only add contention for
+    this memory-bound code; measured here: 64 processes beat 128 on a 64-core/128-thread host)."""
+    n = os.cpu_count() or 1
+    try:
+        out = subprocess.run(["lscpu", "-p=CORE,SOCKET"], capture_output=True, text=True, timeout=10).stdout
+        phys = len({ln for ln in out.splitlines() if ln and not ln.startswith("#")})
+        if 0 < phys <= n:
+            return phys
+    except (OSError, subprocess.SubprocessError):
+        pass
+    return n
+
+
 def cpu_reference_run(images_u8, over, cores):
     """Runs the reference CPU path over `images_u8` ([n,h,w] numpy) with `cores` worker processes (the
     reference is single-threaded: one process per image, as many at a time as there are cores)."""
@@ -178,7 +192,8 @@ def main():
     if args.batch > 0:
         batch = args.batch
     S = over.get("number_of_scales", 3)
-    host_cores = os.cpu_count() or 1
+    host_cores = physical_cores()
+    host_threads = os.cpu_count() or 1
     config = {"workload": "%s: %d x %dx%d u8 gray synthetic textured images per GPU, params %s" %
                           (args.workload, batch, W, H, over or "default"),
               "images_per_gpu": batch, "width": W, "height": H, "params": over,
@@ -347,7 +362,7 @@ def main():
                          "algorithmic_bytes_per_image": blur_bytes, "survey_bytes_per_image_incl_nms": survey_bytes,
                          "traffic": None},
             "clocks": clk,
-            "host_cores": host_cores,
+            "host_cores": host_cores, "host_threads": host_threads,
         }
         if not args.no_cpu_baseline:
             n_cpu = args.cpu_images or min(host_cores, 128, batch)

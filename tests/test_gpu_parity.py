@@ -271,3 +271,41 @@ def test_ellipses_and_sift_file(hb, tmp_path):
     rows = np.array([[float(t) for t in ln.split()] for ln in lines[2:2 + len(k)]])
     assert np.allclose(rows[:, :5], e, rtol=6e-6, atol=1e-9)
     det.close()
+
+
+def test_host_cli_drop_in(hb, tmp_path):
+    """The C++ host (`hesaff <image>`): same stdout line, same <image>.hesaff.sift format as hesaff.cpp:133-180."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "hesaff_b200", "host", "hesaff")
+    if not os.path.exists(exe):
+        pytest.skip("host CLI not built")
+    img = str(tmp_path / "tex.pgm")
+    shutil.copy(os.path.join(GOLDEN, "tex_320x240_s11.pgm"), img)
+    out = subprocess.run([exe, img], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    summ = json.load(open(os.path.join(GOLDEN, "summary.json")))["tex_320x240_s11"]
+    words = out.stdout.split()
+    assert words[0] == "Detected" and int(words[1]) == summ["detections"] and words[2] == "keypoints"
+    assert abs(int(words[4]) - summ["described"]) <= 2 and words[5:8] == ["affine", "shapes", "in"]
+    got = open(img + ".hesaff.sift").read().split("\n")
+    ref = open(os.path.join(GOLDEN, "tex_320x240_s11.hesaff.sift")).read().split("\n")
+    assert got[0] == "128" and abs(int(got[1]) - int(ref[1])) <= 2
+    if got[1] == ref[1]:
+        a = np.array([[float(t) for t in ln.split()] for ln in got[2:2 + int(got[1])]])
+        b = np.array([[float(t) for t in ln.split()] for ln in ref[2:2 + int(ref[1])]])
+        assert np.allclose(a[:, :2], b[:, :2], rtol=1e-5, atol=0)
+        assert np.abs(a[:, 5:] - b[:, 5:]).max() <= 2
+    # colour input (P6) goes through the float path with gray = (R+G+B)/3.0f
+    g = read_pgm(img)
+    ppm = str(tmp_path / "tex.ppm")
+    with open(ppm, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (g.shape[1], g.shape[0]))
+        f.write(np.repeat(g[:, :, None], 3, 2).tobytes())
+    out2 = subprocess.run([exe, ppm], capture_output=True, text=True, timeout=120)
+    assert out2.returncode == 0 and out2.stdout.split()[1] == words[1]
+    assert open(ppm + ".hesaff.sift").read() == open(img + ".hesaff.sift").read()
+    # unreadable file: like the reference, an empty result and exit code 0
+    out3 = subprocess.run([exe, str(tmp_path / "missing.pgm")], capture_output=True, text=True, timeout=60)
+    assert out3.returncode == 0 and open(str(tmp_path / "missing.pgm") + ".hesaff.sift").read() == "128\n0\n"
