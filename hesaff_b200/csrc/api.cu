@@ -543,6 +543,10 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
                                     row_pitch, d_row_pitch, H, cudaMemcpyHostToDevice, st));
          dsrc = L.stage_u8;
       }
+      // Compute of consecutive chunks is serialised (the describe stage already fills the SMs with its own
+      // side-by-side kernels; a second lane's kernels only disturb that packing -- measured); what the second lane
+      // buys is the upload of chunk k+1 and the download of chunk k-1 running under the compute of chunk k.
+      if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
       float *img_plane = L.arena + g.img_off;
       if (is_u8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
@@ -600,8 +604,8 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
 
       // ---- stage 5: ordered compaction into Keypoint records -------------------------------------------
       ha_launch_scan_flags(L.cand.flags, HA_F_DESC, d_count, c->cand_cap, L.desc_off, L.scan_tmp, st, c->lc);
-      // records of this chunk start at the running total of the previous chunks (device-side base): chunk order
-      if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
+      // records of this chunk start at the running total of the previous chunks (device-side base); chunk order is
+      // guaranteed by the wait above
       ha_launch_compact(L.cand, d_count, c->cand_cap, L.desc_off, c->d_geom, c->d_keys, c->d_ell, c->d_ndesc + start,
                         c->d_out_base, (uint32_t)std::min<size_t>(c->keys_cap, 0xFFFFFFFFu), c->d_overflow, st, c->lc);
       uint32_t *d_report = nullptr;
