@@ -317,21 +317,40 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) k_nms(NmsArgs a)
    for (int p = 0; p < 3; p++) { hmax[p][0] = hmax[p][1] = 0.f; hmin[p][0] = hmin[p][1] = 0.f; }
    vcur[0] = vcur[1] = 0.f;
 
-   for (int rr = r0 - 1; rr <= r1; rr++) {
-      const int rl = min(max(rr, 0), a.H - 1);
-      float nmax[3], nmin[3], vnew = 0.f;
+   // software pipeline: the loads of row rr+1 are in flight while row rr is reduced (the shuffles below would
+   // otherwise expose the full memory latency once per row)
+   float nv[3], nl[3], nr[3];
+   {
+      const int rl = min(max(r0 - 1, 0), a.H - 1);
 #pragma unroll
       for (int p = 0; p < 3; p++) {
          const float *row = planes[p] + (size_t)rl * a.pitch;
-         const float v = __ldg(row + cc);
-         float l = __shfl_up_sync(0xffffffffu, v, 1);
-         float r = __shfl_down_sync(0xffffffffu, v, 1);
-         if (lane == 0) l = __ldg(row + cl);
-         if (lane == 31) r = __ldg(row + cr);
-         nmax[p] = fmaxf(fmaxf(l, r), v);
-         nmin[p] = fminf(fminf(l, r), v);
-         if (p == 1) vnew = v;
+         nv[p] = __ldg(row + cc); nl[p] = __ldg(row + cl); nr[p] = __ldg(row + cr);
       }
+   }
+   for (int rr = r0 - 1; rr <= r1; rr++) {
+      float v[3], le[3], re[3];
+#pragma unroll
+      for (int p = 0; p < 3; p++) { v[p] = nv[p]; le[p] = nl[p]; re[p] = nr[p]; }
+      if (rr < r1) {
+         const int rl = min(max(rr + 1, 0), a.H - 1);
+#pragma unroll
+         for (int p = 0; p < 3; p++) {
+            const float *row = planes[p] + (size_t)rl * a.pitch;
+            nv[p] = __ldg(row + cc); nl[p] = __ldg(row + cl); nr[p] = __ldg(row + cr);
+         }
+      }
+      float nmax[3], nmin[3];
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+         float l = __shfl_up_sync(0xffffffffu, v[p], 1);
+         float r = __shfl_down_sync(0xffffffffu, v[p], 1);
+         if (lane == 0) l = le[p];
+         if (lane == 31) r = re[p];
+         nmax[p] = fmaxf(fmaxf(l, r), v[p]);
+         nmin[p] = fminf(fminf(l, r), v[p]);
+      }
+      const float vnew = v[1];
       if (rr >= r0 + 1) {
          const int ro = rr - 1;   // output row: rows ro-1 (age 0), ro (age 1), ro+1 (new) are available
          float M = fmaxf(fmaxf(hmax[0][0], hmax[0][1]), nmax[0]);
