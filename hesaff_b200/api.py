@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
     "hesaff_result_keypoints_device", "hesaff_set_host_output", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
     "hesaff_debug_octave_size", "hesaff_debug_plane", "hesaff_debug_patches", "hesaff_launch_count",
-    "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_write_sift_file",
+    "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_blur_time_ms", "hesaff_write_sift_file",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
         L.hesaff_launch_count.restype = C.c_int64
         L.hesaff_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.hesaff_stage_times_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.hesaff_blur_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.hesaff_write_sift_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_float]
         _lib = L
     return _lib
@@ -252,6 +253,11 @@ class AffineHessianDetector:
 
     def set_profiling(self, on):
         _check(lib().hesaff_set_profiling(self._h, int(on)))
+
+    def blur_time_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        _check(lib().hesaff_blur_time_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def stage_times_ms(self):
         out = np.zeros(6, np.float32)

@@ -40,6 +40,7 @@ struct Lane {
    int *counters;              // [0] affine work, [1..3] describe work
    float *scratch;
    cudaEvent_t ev[8];
+   std::vector<cudaEvent_t> blur_ev;   // profiling: event pairs around every k_blur launch
    cudaEvent_t done;           // recorded after the chunk's k_add_total
    uint32_t *h_total;          // pinned: [0] described keypoints of the last chunk on this lane, [1] base offset
    int pending_chunk;          // chunk index whose results are not yet copied to the host output (-1: none)
@@ -83,6 +84,8 @@ struct hesaff_ctx {
    // profiling (forces single-lane, serialised execution so that stage times are clean)
    bool profiling;
    float stage_ms[6];
+   float blur_ms;              // sum over the k_blur launches of the last call (profiling mode)
+   int blur_launches;
 };
 
 extern "C" int hesaff_abi_version(void) { return HESAFF_B200_ABI_VERSION; }
@@ -193,8 +196,10 @@ static int build_tables(hesaff_ctx *c)
    int rc;
    if ((rc = upload(c, m19, &c->tables.smm_mask))) return rc;
    if ((rc = upload(c, m41, &c->tables.sift_mask))) return rc;
-   // per-patch blur kernels, indexed by m = (P0-1)/2; the patch must fit in the image so P0 <= min(W,H)
-   const int maxP0 = std::min(c->max_w, c->max_h) + 4;
+   // per-patch blur kernels, indexed by m = (P0-1)/2.  interpolateCheckBorders (helpers.cpp:191-207) only accepts a
+   // keypoint whose 41x41 footprint (+-20*its*A, det A = 1) lies inside the image: 40*its*a11 < W and 40*its*a22 < H,
+   // hence its < sqrt(W*H)/40 and P0 = 41*its < 1.025*sqrt(W*H).
+   const int maxP0 = c->maxP;
    const int count = maxP0 / 2 + 2;
    std::vector<int> pn(count, 1), poff(count, 0);
    std::vector<float> pk;
@@ -208,7 +213,7 @@ static int build_tables(hesaff_ctx *c)
       pn[m] = n;
       poff[m] = (int)pk.size();
       for (int i = n / 2; i < n; i++) pk.push_back(k[i]);
-      if (n / 2 > 255) return fail(HESAFF_ERR_INVALID, "image too large for the per-patch blur table");
+      if (n / 2 > HA_MAX_PATCH_R) return fail(HESAFF_ERR_INVALID, "image too large: the per-patch blur would need more than 1039 taps (sqrt(W*H) must stay below ~4600)");
    }
    c->tables.pk_count = count;
    if ((rc = upload(c, pn, &c->tables.pk_n))) return rc;
@@ -280,7 +285,7 @@ template <typename T> static int dmalloc(T **p, size_t n)
 static int alloc_lane(hesaff_ctx *c, Lane &L, const Geom &g)
 {
    int rc;
-   memset(&L, 0, sizeof(L));
+   L = Lane();
    L.pending_chunk = -1;
    CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
    CK(cudaStreamCreateWithFlags(&L.aux, cudaStreamNonBlocking));
@@ -326,7 +331,8 @@ static void free_lane(Lane &L)
    if (L.aux) cudaStreamDestroy(L.aux);
    if (L.h_total) cudaFreeHost(L.h_total);
    if (L.stream) cudaStreamDestroy(L.stream);
-   memset(&L, 0, sizeof(L));
+   for (cudaEvent_t e : L.blur_ev) cudaEventDestroy(e);
+   L = Lane();
 }
 
 extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int device, int max_width, int max_height,
@@ -356,7 +362,6 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    c->d_ndet = c->d_ndesc = nullptr; c->counts_cap = 0; c->d_overflow = nullptr; c->d_out_base = nullptr; c->d_geom = nullptr;
    c->host_out = nullptr; c->host_out_cap = 0; c->host_out_filled = false;
    c->stream = c->copy_stream = nullptr; c->ev_start = nullptr; c->n_lanes = 0;
-   memset(c->lane, 0, sizeof(c->lane));
    memset(c->stage_ms, 0, sizeof(c->stage_ms));
    *out = c;   // so that a failed create can still be destroyed
 
@@ -404,6 +409,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
    CK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
    int rc;
+   c->maxP = (int)(1.025 * sqrt((double)max_width * (double)max_height)) + 10;   // largest source-patch side P = P0 + 2
    if ((rc = build_tables(c))) return rc;
    if ((rc = dmalloc(&c->d_geom, 1))) return rc;
    if ((rc = dmalloc(&c->d_out_base, 2)) || (rc = dmalloc(&c->d_overflow, 2))) return rc;
@@ -411,7 +417,6 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    c->mask_words_cap = g.mask_stride * chunk;
    c->scan_tmp_elems = std::max(ha_scan_tmp_elems(c->mask_words_cap), ha_scan_tmp_elems(c->cand_cap)) + 8;
    c->map_elems_cap = g.map_stride * chunk;
-   c->maxP = std::min(max_width, max_height) + 8;
    c->large_ctas = 148 * 2;
    c->scratch_per_cta = align_up((size_t)c->maxP * 82, 64);
    for (int l = 0; l < c->n_lanes; l++)
@@ -510,6 +515,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int) * 2, ust));
    CK(cudaEventRecord(c->ev_start, ust));
    memset(c->stage_ms, 0, sizeof(c->stage_ms));
+   c->blur_ms = 0.f; c->blur_launches = 0;
    c->n_images = n;
    c->last_chunks = 0;
    const int S = g.S;
@@ -553,7 +559,14 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
       if (c->profiling) cudaEventRecord(L.ev[1], st);
 
       // ---- stage 1: pyramid (pyramid.cpp:261-292, 224-259) ------------------------------------------
+      size_t bev = 0;
+      auto blur_mark = [&]() {   // profiling: an event before and after every blur launch
+         if (!c->profiling) return;
+         if (bev >= L.blur_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); L.blur_ev.push_back(e); }
+         cudaEventRecord(L.blur_ev[bev++], st);
+      };
       if (g.nOct > 0) {
+         blur_mark();
          float *L00 = L.arena + g.L_off[0][0], *R00 = L.arena + g.R_off[0][0];
          if (c->taps0.n > 0) {
             if (ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0],
@@ -564,6 +577,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
             ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0], id,
                            cn, st, c->lc);
          }
+         blur_mark();
       }
       for (int o = 0; o < g.nOct; o++) {
          if (o > 0)   // response of the decimated first level (cur = hessianResponse(blur, sigma0^2), pyramid.cpp:230)
@@ -572,10 +586,12 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
          for (int i = 1; i < S + 2; i++) {
             const bool seed_next = (i == S) && (o + 1 < g.nOct);   // halfImage(nextBlur) at i == numberOfScales
             float *half = seed_next ? L.arena + g.L_off[o + 1][0] : nullptr;
+            blur_mark();
             if (ha_launch_blur(L.arena + g.L_off[o][i - 1], L.arena + g.L_off[o][i], L.arena + g.R_off[o][i], half, g.w[o],
                                g.h[o], g.pitch[o], seed_next ? g.w[o + 1] : 0, seed_next ? g.h[o + 1] : 0,
                                seed_next ? g.pitch[o + 1] : 0, g.arena_stride, c->norm[i], c->taps[i], cn, st, c->lc))
                return fail(HESAFF_ERR_INVALID, "unsupported blur size");
+            blur_mark();
          }
       }
       if (c->profiling) cudaEventRecord(L.ev[2], st);
@@ -622,6 +638,12 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
             float ms = 0;
             cudaEventElapsedTime(&ms, L.ev[q], L.ev[q + 1]);
             c->stage_ms[q] += ms;
+         }
+         for (size_t q = 0; q + 1 < bev; q += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, L.blur_ev[q], L.blur_ev[q + 1]);
+            c->blur_ms += ms;
+            c->blur_launches++;
          }
       }
    }
@@ -802,6 +824,14 @@ extern "C" int hesaff_stage_times_ms(hesaff_ctx *c, float *out6)
 {
    if (!c || !out6) return fail(HESAFF_ERR_INVALID, "NULL argument");
    memcpy(out6, c->stage_ms, sizeof(c->stage_ms));
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_blur_time_ms(hesaff_ctx *c, float *total_ms, int *launches)
+{
+   if (!c) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   if (total_ms) *total_ms = c->blur_ms;
+   if (launches) *launches = c->blur_launches;
    return HESAFF_OK;
 }
 

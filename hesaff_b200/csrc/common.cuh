@@ -16,6 +16,8 @@
 #define HA_SMM 19              // SMM window side (affine.h:43)
 #define HA_SMM_PX (HA_SMM * HA_SMM)
 
+#define HA_MAX_PATCH_R 519     // largest half-width of a per-patch blur kernel (shared-memory table)
+
 #define HA_BIN_SMALL_MAXP 47   // patch+SIFT kernel bins by source-patch side P
 #define HA_BIN_MEDIUM_MAXP 95
 

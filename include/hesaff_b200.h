@@ -150,6 +150,9 @@ int64_t hesaff_launch_count(hesaff_ctx *ctx, int reset);
  * [4] patch+SIFT, [5] compaction/export.  Requires hesaff_set_profiling(ctx, 1) before the call. */
 int hesaff_set_profiling(hesaff_ctx *ctx, int enable);
 int hesaff_stage_times_ms(hesaff_ctx *ctx, float *out6);
+/* Sum of the CUDA-event durations of the individual blur+response launches (K1) of the last profiled call, and their
+ * number: the per-launch figure bench.py's roofline uses. */
+int hesaff_blur_time_ms(hesaff_ctx *ctx, float *total_ms, int *launches);
 
 /* Text export of one image's keypoints in the reference's file format (hesaff.cpp:107-130,
  * README:27-44): "128\n<count>\n" then "x y a b c d1..d128" per line with ostream default

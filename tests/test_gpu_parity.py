@@ -309,3 +309,40 @@ def test_host_cli_drop_in(hb, tmp_path):
     # unreadable file: like the reference, an empty result and exit code 0
     out3 = subprocess.run([exe, str(tmp_path / "missing.pgm")], capture_output=True, text=True, timeout=60)
     assert out3.returncode == 0 and open(str(tmp_path / "missing.pgm") + ".hesaff.sift").read() == "128\n0\n"
+
+
+@pytest.mark.parametrize("w,h,seed,over,crop", [
+    (3840, 2160, 3, {"number_of_scales": 10, "max_octaves": 3}, (1408, 704, 1024, 768)),     # BASELINE configs[1]
+    (4096, 4096, 5, {"threshold": 5.0, "max_octaves": 6}, (2048, 1024, 1024, 1024)),          # BASELINE configs[4]
+])
+def test_full_size_configs_match_oracle_on_an_interior_crop(hb, port_oracle, w, h, seed, over, crop):
+    """Full BASELINE sizes through a size-independent property: every stage has finite support, so keypoints of the low
+    octaves that lie well inside an octave-aligned crop are the same whether the path runs on the full frame (GPU) or
+    on the crop alone (oracle, seconds).  Also: identical frames in one batch give identical records."""
+    img = textured(w, h, seed)
+    det = run(hb, np.stack([img, img]), **over)
+    k = det.keys()
+    o = det.offsets()
+    assert k[o[0]:o[1]].tobytes() == k[o[1]:o[2]].tobytes()
+    k = k[o[0]:o[1]]
+    assert 10000 * (w * h / 1e6) < len(k) < 60000 * (w * h / 1e6)         # textured images: ~16-30 k keypoints / Mpix
+    x0, y0, cw, ch = crop
+    assert x0 % 32 == 0 and y0 % 32 == 0
+    want = port_oracle.detect(img[y0:y0 + ch, x0:x0 + cw].astype(np.float32), oparams(port_oracle, over))
+    want = want[(want["described"] == 1) & (want["pd"] <= 4)]
+    m = 320                                                                   # > blur + SMM + patch support at pd <= 4
+    inside = lambda x, y: (x > m) & (x < cw - m) & (y > m) & (y < ch - m)     # noqa: E731
+    want = want[inside(want["x"], want["y"])]
+    got = k[inside(k["x"] - x0, k["y"] - y0)].copy()
+    got["x"] -= x0
+    got["y"] -= y0
+    # low octaves only (the GPU record has no pd; scale bounds it: s < sigma_max * 4 for pd <= 4)
+    from scipy.spatial import cKDTree
+    t = cKDTree(np.stack([got["x"], got["y"], got["s"]], 1))
+    d, j = t.query(np.stack([want["x"], want["y"], want["s"]], 1))
+    assert len(want) > 1000
+    matched = d < 2e-3
+    assert matched.mean() >= 0.995, matched.mean()
+    st = compare_keypoints(got[j[matched]], want[matched], mr_size=det.par.desc_factor)
+    assert st["within_tol_frac"] >= 0.995, st
+    det.close()
