@@ -141,6 +141,27 @@ def _cpu_worker(args):
     return time.perf_counter() - t, int(len(d)), int(d["described"].sum())
 
 
+def ncu_traffic():
+    """DRAM bytes (read+write) of one octave-0 k_blur_tma launch from the committed `ncu --set full` capture
+    (profiles/r1b_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
+    path = os.path.join(ROOT, "profiles", "r1b_k_blur_tma_ncu.txt")
+    try:
+        rd = wr = None
+        for line in open(path):
+            t = line.split()
+            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(t[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+                if t[0].startswith("dram__bytes_read") and rd is None:
+                    rd = v
+                elif t[0].startswith("dram__bytes_write") and wr is None:
+                    wr = v
+            if rd is not None and wr is not None:
+                return rd + wr, 32 * 1920 * 1080 * 12.0
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def physical_cores():
     """Worker count for the CPU reference: one process per physical core (SMT siblings only add contention for
     this memory-bound code; measured here: 64 processes beat 128 on a 64-core/128-thread host)."""
@@ -364,7 +385,10 @@ def main():
                          "frac": achieved / peak if peak else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_image": blur_bytes, "survey_bytes_per_image_incl_nms": survey_bytes,
-                         "traffic": None},
+                         "traffic": ncu_traffic()[0],
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE octave-0 k_blur_tma<11> launch over "
+                                         "32 x 1920x1080 (ncu --set full, profiles/r1b_k_blur_tma_ncu.txt); algorithmic bytes of "
+                                         "that launch: %.0f" % (ncu_traffic()[1] or 0)},
             "clocks": clk,
             "host_cores": host_cores, "host_threads": host_threads,
         }
