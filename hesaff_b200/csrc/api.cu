@@ -397,7 +397,9 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    // two lanes of `chunk` images each; a batch that fits one chunk (max_batch given and small) still gets 2 lanes of
    // that size so that consecutive calls need no reallocation
    int chunk = max_batch;
-   if (chunk <= 0) chunk = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)(free_b * 0.45) / (2 * pib)));
+   size_t chunk_cap = 128;   // large chunks amortise the launch-bound small octaves (pyramid stage: 50 -> 40 ms per 1024 x 1080p)
+   if (const char *e = getenv("HESAFF_CHUNK")) chunk_cap = (size_t)std::max(1, atoi(e));   // tuning knob (bench experiments)
+   if (chunk <= 0) chunk = (int)std::min<size_t>(chunk_cap, std::max<size_t>(1, (size_t)(free_b * 0.45) / (2 * pib)));
    c->n_lanes = 2;
    if ((size_t)chunk * pib * 2 > free_b * 0.85) c->n_lanes = 1;
    if ((size_t)chunk * pib * c->n_lanes > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");

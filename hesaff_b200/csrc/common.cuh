@@ -136,7 +136,8 @@ int ha_launch_blur(const float *src, float *dstL, float *dstR, float *half, int 
                    int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
                    LaunchCounter &lc);
 int ha_launch_blur_tma(const float *src, float *dstL, float *dstR, float *half, int W, int H, int pitch, int hW, int hH,
-                       int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st);
+                       int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
+                       int variant = 0);
 void ha_launch_hessian(const float *src, float *dst, int W, int H, int pitch, unsigned long long img_stride, float norm,
                        int n, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_nms(const float *arena, const Geom &g, const Geom *dg, uint32_t *mask, int n, cudaStream_t st,
