@@ -164,3 +164,4 @@ void ha_launch_compact(Cand cand, const uint32_t *count, uint32_t cap, const uin
 void ha_launch_export_detections(Cand cand, const uint32_t *count, uint32_t cap, const uint32_t *det_off,
                                  const Geom *dg, hesaff_detection *out, cudaStream_t st, LaunchCounter &lc);
 int ha_describe_smem_bytes(int bin, int maxP);
+size_t ha_describe_scratch_floats(int maxP);
