@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "hesaff_result_keypoints_device", "hesaff_set_host_output", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
     "hesaff_debug_octave_size", "hesaff_debug_plane", "hesaff_debug_patches", "hesaff_launch_count",
     "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_blur_time_ms", "hesaff_write_sift_file",
+    "hesaff_result_sift_text", "hesaff_export_sift_file", "hesaff_write_keypoints_binary", "hesaff_read_keypoints_binary",
+    "hesaff_debug_format_floats",
 ]
 
 
@@ -90,6 +92,11 @@ def lib():
         L.hesaff_stage_times_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.hesaff_blur_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.hesaff_write_sift_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_float]
+        L.hesaff_result_sift_text.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.hesaff_export_sift_file.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.hesaff_write_keypoints_binary.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
+        L.hesaff_read_keypoints_binary.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.hesaff_debug_format_floats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -218,12 +225,37 @@ class AffineHessianDetector:
         _check(lib().hesaff_result_detections(self._h, out.ctypes.data, len(out), C.byref(nt)))
         return out
 
-    def exportKeypoints(self, path, image=0):
-        """Writes <path> in the reference's .hesaff.sift format (hesaff.cpp:107-130) for one image."""
+    def exportKeypoints(self, path, image=0, on_host=False):
+        """Writes <path> in the reference's .hesaff.sift format (hesaff.cpp:107-130) for one image.  The text is
+        formatted on the GPU (hesaff_export_sift_file); on_host=True uses the host ostream writer instead (same bytes)."""
+        if not on_host:
+            return _check(lib().hesaff_export_sift_file(self._h, image, path.encode()))
         k = self.keys()
         o = self.offsets()
         k = np.ascontiguousarray(k[o[image]:o[image + 1]])
         return _check(lib().hesaff_write_sift_file(path.encode(), k.ctypes.data, len(k), self.par.desc_factor))
+
+    def siftText(self, image=0):
+        """The .hesaff.sift file content of one image as bytes, formatted on the GPU."""
+        nb = C.c_size_t()
+        _check(lib().hesaff_result_sift_text(self._h, image, None, 0, C.byref(nb)))
+        buf = C.create_string_buffer(nb.value)
+        _check(lib().hesaff_result_sift_text(self._h, image, buf, nb.value, C.byref(nb)))
+        return buf.raw[:nb.value]
+
+    def exportKeypointsBinary(self, path, image=0):
+        """Binary sidecar (hesaff_write_keypoints_binary): header + the 164-byte Keypoint records of one image."""
+        k = self.keys()
+        o = self.offsets()
+        k = np.ascontiguousarray(k[o[image]:o[image + 1]])
+        return _check(lib().hesaff_write_keypoints_binary(path.encode(), k.ctypes.data, len(k)))
+
+    def formatFloats(self, values):
+        """Diagnostic: the device "%g" formatter on an array of float32 (list of str)."""
+        v = np.ascontiguousarray(values, np.float32)
+        out = np.zeros((len(v), 16), np.uint8)
+        _check(lib().hesaff_debug_format_floats(self._h, v.ctypes.data, len(v), out.ctypes.data))
+        return [bytes(r).split(b"\0")[0].decode() for r in out]
 
     # ---- stage access (tests) ----
     def geometry(self):

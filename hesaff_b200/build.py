@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhesaff_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu", "export.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "hesaff_b200.h")]
 
 NVCC_FLAGS = [

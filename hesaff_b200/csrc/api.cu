@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <fstream>
+#include <sstream>
 #include "common.cuh"
 
 static thread_local std::string g_err;
@@ -76,6 +77,9 @@ struct hesaff_ctx {
    hesaff_keypoint *d_keys; float *d_ell; size_t keys_cap;
    uint32_t *d_out_base;       // running total of described keypoints over chunks
    hesaff_detection *d_dets; size_t dets_cap;
+   char *d_text; size_t text_cap;            // GPU-formatted .hesaff.sift lines of one image
+   uint32_t *d_tlen, *d_toff; size_t tlen_cap;
+   int *d_bad;
    hesaff_keypoint *host_out; size_t host_out_cap; bool host_out_filled;   // optional streamed host output
    int64_t total_desc, total_det;
    int last_chunks;
@@ -358,7 +362,8 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    hesaff_ctx *c = new hesaff_ctx();
    c->par = *p; c->device = device; c->max_w = max_width; c->max_h = max_height;
    c->have_result = false; c->profiling = false; c->lc.n = 0;
-   c->d_dets = nullptr; c->dets_cap = 0; c->d_keys = nullptr; c->d_ell = nullptr; c->keys_cap = 0;
+   c->d_dets = nullptr; c->dets_cap = 0; c->d_text = nullptr; c->text_cap = 0; c->d_tlen = c->d_toff = nullptr; c->tlen_cap = 0;
+   c->d_bad = nullptr; c->d_keys = nullptr; c->d_ell = nullptr; c->keys_cap = 0;
    c->d_ndet = c->d_ndesc = nullptr; c->counts_cap = 0; c->d_overflow = nullptr; c->d_out_base = nullptr; c->d_geom = nullptr;
    c->host_out = nullptr; c->host_out_cap = 0; c->host_out_filled = false;
    c->stream = c->copy_stream = nullptr; c->ev_start = nullptr; c->n_lanes = 0;
@@ -433,7 +438,8 @@ extern "C" int hesaff_destroy(hesaff_ctx *c)
    if (c->stream) cudaStreamSynchronize(c->stream);
    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
    for (int l = 0; l < 2; l++) free_lane(c->lane[l]);
-   void *ptrs[] = {c->d_geom, c->d_out_base, c->d_overflow, c->d_ndet, c->d_ndesc, c->d_keys, c->d_ell, c->d_dets};
+   void *ptrs[] = {c->d_geom, c->d_out_base, c->d_overflow, c->d_ndet, c->d_ndesc, c->d_keys, c->d_ell, c->d_dets,
+                   c->d_text, c->d_tlen, c->d_toff, c->d_bad};
    for (void *p : ptrs) if (p) cudaFree(p);
    for (void *p : c->table_allocs) cudaFree(p);
    if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -838,13 +844,8 @@ extern "C" int hesaff_blur_time_ms(hesaff_ctx *c, float *total_ms, int *launches
 }
 
 // exportKeypoints, hesaff.cpp:107-130 (text formatting on the host; ostream defaults = 6 significant digits)
-extern "C" int hesaff_write_sift_file(const char *path, const hesaff_keypoint *kps, size_t n, float desc_factor)
+static void format_sift_lines_host(std::ostream &out, const hesaff_keypoint *kps, size_t n, float desc_factor)
 {
-   if (!path || (!kps && n)) return fail(HESAFF_ERR_INVALID, "NULL argument");
-   std::ofstream out(path);
-   if (!out) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
-   out << 128 << std::endl;
-   out << n << std::endl;
    for (size_t i = 0; i < n; i++) {
       const hesaff_keypoint &k = kps[i];
       const double sc = (double)(desc_factor * k.s);
@@ -854,7 +855,163 @@ extern "C" int hesaff_write_sift_file(const char *path, const hesaff_keypoint *k
       out << k.x << " " << k.y << " " << (float)(r / det * isc2) << " " << (float)(-q / det * isc2) << " "
           << (float)(p / det * isc2);
       for (size_t j = 0; j < 128; j++) out << " " << int(k.desc[j]);
-      out << std::endl;
+      out << "\n";
    }
+}
+
+extern "C" int hesaff_write_sift_file(const char *path, const hesaff_keypoint *kps, size_t n, float desc_factor)
+{
+   if (!path || (!kps && n)) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   std::ofstream out(path);
+   if (!out) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
+   out << 128 << "\n" << n << "\n";
+   format_sift_lines_host(out, kps, n, desc_factor);
+   out.flush();
+   if (!out) return fail(HESAFF_ERR_INVALID, std::string("write failed: ") + path);
    return (int)n;
+}
+
+// ---- GPU-side text export -------------------------------------------------------------------
+// first record and count of image `image` in the image-major output
+static void image_range(const hesaff_ctx *c, int image, size_t &first, size_t &n)
+{
+   first = 0;
+   for (int i = 0; i < image; i++) first += (size_t)c->h_ndesc[i];
+   n = (size_t)c->h_ndesc[image];
+}
+
+extern "C" int hesaff_result_sift_text(hesaff_ctx *c, int image, char *out, size_t capacity, size_t *nbytes)
+{
+   NEED_RESULT(c);
+   if (image < 0 || image >= c->n_images) return fail(HESAFF_ERR_INVALID, "bad image index");
+   size_t first, n;
+   image_range(c, image, first, n);
+   char header[64];
+   const int hl = snprintf(header, sizeof(header), "128\n%zu\n", n);
+   cudaStream_t st = c->stream;
+   int rc;
+   if (n + 1 > c->tlen_cap) {
+      if (c->d_tlen) cudaFree(c->d_tlen);
+      if (c->d_toff) cudaFree(c->d_toff);
+      c->d_tlen = c->d_toff = nullptr;
+      c->tlen_cap = 0;
+      if ((rc = dmalloc(&c->d_tlen, n + 1)) || (rc = dmalloc(&c->d_toff, n + 2))) return rc;
+      c->tlen_cap = n + 1;
+   }
+   if (!c->d_bad && (rc = dmalloc(&c->d_bad, 1))) return rc;
+   uint32_t body = 0;
+   int bad = 0;
+   if (n) {
+      if (ha_scan_tmp_elems(n) > c->scan_tmp_elems) return fail(HESAFF_ERR_CAPACITY, "scan scratch too small for this image");
+      CK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), st));
+      ha_launch_sift_text(false, c->d_keys + first, c->d_ell + first * 5, (uint32_t)n, c->d_tlen, nullptr, nullptr, c->d_bad, st, c->lc);
+      ha_launch_scan_u32(c->d_tlen, n, c->d_toff, c->lane[0].scan_tmp, st, c->lc);
+      CK(cudaMemcpyAsync(&body, c->d_toff + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+   }
+   if (bad) {
+      // a value outside the device formatter's range (inf / nan / >= 2^63): format this image on the host
+      std::vector<hesaff_keypoint> k(n);
+      CK(cudaMemcpy(k.data(), c->d_keys + first, sizeof(hesaff_keypoint) * n, cudaMemcpyDeviceToHost));
+      std::ostringstream os;
+      format_sift_lines_host(os, k.data(), n, c->par.desc_factor);
+      const std::string s = os.str();
+      if (nbytes) *nbytes = (size_t)hl + s.size();
+      if (!out) return HESAFF_OK;
+      if ((size_t)hl + s.size() > capacity) return fail(HESAFF_ERR_CAPACITY, "text buffer too small");
+      memcpy(out, header, hl);
+      memcpy(out + hl, s.data(), s.size());
+      return HESAFF_OK;
+   }
+   if (nbytes) *nbytes = (size_t)hl + body;
+   if (!out) return HESAFF_OK;
+   if ((size_t)hl + body > capacity) return fail(HESAFF_ERR_CAPACITY, "text buffer too small");
+   memcpy(out, header, hl);
+   if (n) {
+      if ((size_t)body > c->text_cap) {
+         if (c->d_text) cudaFree(c->d_text);
+         c->d_text = nullptr;
+         c->text_cap = 0;
+         if ((rc = dmalloc(&c->d_text, (size_t)body + 64))) return rc;
+         c->text_cap = (size_t)body + 64;
+      }
+      ha_launch_sift_text(true, c->d_keys + first, c->d_ell + first * 5, (uint32_t)n, nullptr, c->d_toff, c->d_text, c->d_bad, st, c->lc);
+      CK(cudaMemcpyAsync(out + hl, c->d_text, body, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+   }
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_export_sift_file(hesaff_ctx *c, int image, const char *path)
+{
+   NEED_RESULT(c);
+   if (!path) return fail(HESAFF_ERR_INVALID, "NULL path");
+   size_t nb = 0;
+   int rc = hesaff_result_sift_text(c, image, nullptr, 0, &nb);
+   if (rc) return rc;
+   std::vector<char> buf(nb);
+   if ((rc = hesaff_result_sift_text(c, image, buf.data(), buf.size(), &nb))) return rc;
+   FILE *f = fopen(path, "wb");
+   if (!f) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
+   const size_t w = fwrite(buf.data(), 1, nb, f);
+   if (fclose(f) != 0 || w != nb) return fail(HESAFF_ERR_INVALID, std::string("write failed: ") + path);
+   return c->h_ndesc[image];
+}
+
+// Binary sidecar: "HESAFFB1", u32 record size (164), u32 reserved, u64 count, then the Keypoint records.
+extern "C" int hesaff_write_keypoints_binary(const char *path, const hesaff_keypoint *kps, size_t n)
+{
+   if (!path || (!kps && n)) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   FILE *f = fopen(path, "wb");
+   if (!f) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
+   const uint32_t hdr[2] = {(uint32_t)sizeof(hesaff_keypoint), 0u};
+   const uint64_t cnt = n;
+   bool ok = fwrite("HESAFFB1", 1, 8, f) == 8 && fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(&cnt, sizeof(cnt), 1, f) == 1;
+   ok = ok && (n == 0 || fwrite(kps, sizeof(hesaff_keypoint), n, f) == n);
+   if (fclose(f) != 0 || !ok) return fail(HESAFF_ERR_INVALID, std::string("write failed: ") + path);
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_read_keypoints_binary(const char *path, hesaff_keypoint *out, size_t capacity, size_t *n)
+{
+   if (!path || !n) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   FILE *f = fopen(path, "rb");
+   if (!f) return fail(HESAFF_ERR_INVALID, std::string("cannot open ") + path);
+   char magic[8];
+   uint32_t hdr[2];
+   uint64_t cnt = 0;
+   bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, "HESAFFB1", 8) && fread(hdr, sizeof(hdr), 1, f) == 1 &&
+             hdr[0] == sizeof(hesaff_keypoint) && fread(&cnt, sizeof(cnt), 1, f) == 1;
+   if (!ok) { fclose(f); return fail(HESAFF_ERR_INVALID, std::string("not a hesaff binary keypoint file: ") + path); }
+   *n = (size_t)cnt;
+   if (!out) { fclose(f); return HESAFF_OK; }
+   if (cnt > capacity) { fclose(f); return fail(HESAFF_ERR_CAPACITY, "output capacity too small"); }
+   ok = cnt == 0 || fread(out, sizeof(hesaff_keypoint), cnt, f) == cnt;
+   fclose(f);
+   if (!ok) return fail(HESAFF_ERR_INVALID, std::string("truncated file: ") + path);
+   return HESAFF_OK;
+}
+
+// Diagnostic: the device float formatter on its own; out receives n slots of 16 bytes, NUL padded ("?" = not covered).
+extern "C" int hesaff_debug_format_floats(hesaff_ctx *c, const float *in, size_t n, char *out)
+{
+   if (!c || !in || !out) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   CK(cudaSetDevice(c->device));
+   if (!n) return HESAFF_OK;
+   float *d_in = nullptr;
+   char *d_out = nullptr;
+   int rc;
+   if ((rc = dmalloc(&d_in, n))) return rc;
+   if ((rc = dmalloc(&d_out, n * 16))) { cudaFree(d_in); return rc; }
+   cudaError_t e = cudaMemcpy(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice);
+   if (e == cudaSuccess) {
+      ha_launch_format_floats(d_in, n, d_out, c->stream);
+      e = cudaStreamSynchronize(c->stream);
+   }
+   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost);
+   cudaFree(d_in);
+   cudaFree(d_out);
+   CK(e);
+   return HESAFF_OK;
 }

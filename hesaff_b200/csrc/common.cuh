@@ -147,7 +147,12 @@ void ha_launch_scan_popc(const uint32_t *words, size_t nwords, uint32_t *out, ui
                          LaunchCounter &lc);
 void ha_launch_scan_flags(const unsigned char *flags, unsigned char bit, const uint32_t *count_ptr, size_t cap,
                           uint32_t *out, uint32_t *tmp, cudaStream_t st, LaunchCounter &lc);
+void ha_launch_scan_u32(const uint32_t *vals, size_t n, uint32_t *out, uint32_t *tmp, cudaStream_t st, LaunchCounter &lc);
 size_t ha_scan_tmp_elems(size_t n);
+// export.cu: text lines of the .hesaff.sift file (length pass / write pass), and the float formatter on its own
+void ha_launch_sift_text(bool write, const hesaff_keypoint *keys, const float *ell, uint32_t n, uint32_t *len,
+                         const uint32_t *off, char *text, int *bad, cudaStream_t st, LaunchCounter &lc);
+void ha_launch_format_floats(const float *in, size_t n, char *out, cudaStream_t st);
 void ha_launch_expand(const uint32_t *mask, const uint32_t *woff, const Geom *dg, size_t nwords, Cand cand, uint32_t cap,
                       int *overflow, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_localize(const float *arena, const Geom *dg, Cand cand, const uint32_t *count, uint32_t cap,

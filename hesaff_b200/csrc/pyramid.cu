@@ -414,6 +414,12 @@ struct FlagIn {
    }
 };
 
+struct U32In {
+   const uint32_t *v;
+   size_t n;
+   __device__ uint32_t operator()(size_t i) const { return i < n ? v[i] : 0u; }
+};
+
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t &total)
 {
    __shared__ uint32_t wsum[SCAN_T / 32];
@@ -501,6 +507,12 @@ void ha_launch_scan_popc(const uint32_t *words, size_t nwords, uint32_t *out, ui
 {
    PopcIn in{words, nwords};
    scan_generic(in, nwords, out, tmp, st, lc);
+}
+
+void ha_launch_scan_u32(const uint32_t *vals, size_t n, uint32_t *out, uint32_t *tmp, cudaStream_t st, LaunchCounter &lc)
+{
+   U32In in{vals, n};
+   scan_generic(in, n, out, tmp, st, lc);
 }
 
 void ha_launch_scan_flags(const unsigned char *flags, unsigned char bit, const uint32_t *count_ptr, size_t cap, uint32_t *out,

@@ -101,6 +101,7 @@ int main(int argc, char **argv)
       vector<hesaff_keypoint> keys;
       int nDetected = 0, nAffine = 0;
       double t1 = 0, elapsed = 0;
+      bool written = false;
       if (readPNM(files[fi], w, h, gray, rgb)) {
          hesaff_ctx *ctx = 0;
          int rc = hesaff_create(&ctx, &p, device, w, h, 1, 0);
@@ -121,6 +122,15 @@ int main(int argc, char **argv)
                if (rc == HESAFF_OK && !keys.empty()) rc = hesaff_result_keypoints(ctx, keys.data(), keys.size());
                elapsed = wallTime() - t1;
             }
+            // exportKeypoints (hesaff.cpp:169-173), with the text formatted on the GPU; the reference times only the
+            // detector (hesaff.cpp:166-168), and so does the line below
+            if (rc == HESAFF_OK) {
+               const string out = string(files[fi]) + ".hesaff.sift";
+               if (hesaff_export_sift_file(ctx, 0, out.c_str()) >= 0) written = true;
+               else rc = HESAFF_ERR_INVALID;
+               if (rc == HESAFF_OK && getenv("HESAFF_BINARY_SIDECAR"))
+                  rc = hesaff_write_keypoints_binary((string(files[fi]) + ".hesaff.bin").c_str(), keys.data(), keys.size());
+            }
          }
          if (rc != HESAFF_OK) {
             fprintf(stderr, "hesaff_b200: %s\n", hesaff_last_error());
@@ -132,7 +142,7 @@ int main(int argc, char **argv)
       // an unreadable file behaves like the reference: empty image -> "128\n0\n", exit code 0
       cout << "Detected " << nDetected << " keypoints and " << nAffine << " affine shapes in " << elapsed << " sec." << endl;
       string out = string(files[fi]) + ".hesaff.sift";
-      if (hesaff_write_sift_file(out.c_str(), keys.data(), keys.size(), par.desc_factor) < 0) {
+      if (!written && hesaff_write_sift_file(out.c_str(), keys.data(), keys.size(), par.desc_factor) < 0) {
          fprintf(stderr, "hesaff_b200: %s\n", hesaff_last_error());
          status = 1;
       }

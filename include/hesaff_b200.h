@@ -159,6 +159,20 @@ int hesaff_blur_time_ms(hesaff_ctx *ctx, float *total_ms, int *launches);
  * formatting (6 significant digits).  Writes the file; returns the number of keypoints or <0. */
 int hesaff_write_sift_file(const char *path, const hesaff_keypoint *kps, size_t n, float desc_factor);
 
+/* The same file content for image `image` of the last detect call, formatted ON THE GPU (one warp per keypoint;
+ * float -> text is the exact "%g" conversion of ostream, so the bytes equal hesaff_write_sift_file's).  At GPU
+ * detection rates the host's ostream loop of exportKeypoints (hesaff.cpp:107-130) would dominate the CLI.
+ *   hesaff_result_sift_text: header + lines into `out` (host memory); out == NULL only reports the size in *nbytes.
+ *   hesaff_export_sift_file: writes the file; returns the number of keypoints or <0. */
+int hesaff_result_sift_text(hesaff_ctx *ctx, int image, char *out, size_t capacity, size_t *nbytes);
+int hesaff_export_sift_file(hesaff_ctx *ctx, int image, const char *path);
+/* Binary sidecar for consumers that do not want text: "HESAFFB1", u32 record size (164), u32 0, u64 count, then
+ * the hesaff_keypoint records.  read: out == NULL only reports the count in *n. */
+int hesaff_write_keypoints_binary(const char *path, const hesaff_keypoint *kps, size_t n);
+int hesaff_read_keypoints_binary(const char *path, hesaff_keypoint *out, size_t capacity, size_t *n);
+/* Diagnostic: the device float formatter on n floats; out = n slots of 16 bytes, NUL padded. */
+int hesaff_debug_format_floats(hesaff_ctx *ctx, const float *in, size_t n, char *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,3 +346,53 @@ def test_full_size_configs_match_oracle_on_an_interior_crop(hb, port_oracle, w, 
     st = compare_keypoints(got[j[matched]], want[matched], mr_size=det.par.desc_factor)
     assert st["within_tol_frac"] >= 0.995, st
     det.close()
+
+
+def test_gpu_text_export_equals_host_writer(hb, tmp_path):
+    """the .hesaff.sift text formatted on the GPU is byte-identical to the host ostream writer
+    (exportKeypoints, hesaff.cpp:107-130) on the same keypoints, for every image of a batch; binary sidecar round trip."""
+    imgs = np.stack([textured(320, 240, 11), textured(320, 240, 12), np.zeros((240, 320), np.uint8)])
+    det = run(hb, imgs)
+    k, off = det.keys(), det.offsets()
+    for i in range(len(imgs)):
+        host, gpu = str(tmp_path / ("h%d.sift" % i)), str(tmp_path / ("g%d.sift" % i))
+        assert det.exportKeypoints(host, image=i, on_host=True) == off[i + 1] - off[i]
+        assert det.exportKeypoints(gpu, image=i) == off[i + 1] - off[i]
+        a, b = open(host, "rb").read(), open(gpu, "rb").read()
+        assert a == b, "image %d: GPU text differs from the host writer" % i
+        assert det.siftText(i) == a
+    assert open(str(tmp_path / "g2.sift")).read() == "128\n0\n"
+    bpath = str(tmp_path / "k.bin")
+    det.exportKeypointsBinary(bpath, image=1)
+    raw = open(bpath, "rb").read()
+    assert raw[:8] == b"HESAFFB1" and len(raw) == 24 + 164 * (off[2] - off[1])
+    back = np.frombuffer(raw[24:], hb.KEYPOINT_DTYPE)
+    assert np.array_equal(back, k[off[1]:off[2]])
+    n = hb.api.C.c_size_t()
+    out = np.zeros(off[2] - off[1], hb.KEYPOINT_DTYPE)
+    assert hb.lib().hesaff_read_keypoints_binary(bpath.encode(), out.ctypes.data, len(out), hb.api.C.byref(n)) == 0
+    assert n.value == len(out) and np.array_equal(out, back)
+    det.close()
+
+
+def test_gpu_float_formatter_is_exact_percent_g(hb):
+    """The device formatter against the host's correctly rounded "%g" (what ostream << float prints): random bit
+    patterns over all finite magnitudes below 2^63, decimal ties, the %e/%f switch-over points, denormals, zeros."""
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 0x5F000000, 200000, dtype=np.uint32) | (rng.integers(0, 2, 200000, dtype=np.uint32) << 31)
+    vals = [bits.view(np.float32)]
+    vals.append(np.float32([0.0, -0.0, 1.0, 0.5, 123456.5, 123457.5, 999999.5, 999999.4, 1e6, 1234565.0, 1234575.0, 1e-4, 9.99999e-5,
+                            9.999995e-5, 0.0001, 0.00012345675, 1e-5, 1.4e-45, 1.17549435e-38, 3.4e-39, 2.5, 0.125, 100000.0,
+                            99999.95, 99999.94, 12345.675, 8388608.0, 16777216.0, 9.2e18, 7.0, 10.0, 1e10, 1.5e-10, 65504.0]))
+    vals.append((rng.random(50000) * 4096).astype(np.float32))                      # coordinates
+    vals.append((10.0 ** rng.uniform(-9, 0, 50000)).astype(np.float32))             # ellipse entries
+    vals.append((rng.integers(0, 2 ** 24, 20000) / 2.0).astype(np.float32))         # x.5 values: ties at 6+ digits
+    v = np.concatenate(vals)
+    det = hb.AffineHessianDetector(hb.HessianAffineParams(), device=0, max_width=64, max_height=64, max_batch=1)
+    got = det.formatFloats(v)
+    want = ["%g" % float(x) for x in v]
+    bad = [(float(x), g, w) for x, g, w in zip(v, got, want) if g != w]
+    assert not bad, bad[:10]
+    # values the device path does not cover are flagged, not misprinted
+    assert det.formatFloats(np.float32([np.inf, np.nan, 1e19])) == ["?", "?", "?"]
+    det.close()
