@@ -26,7 +26,7 @@ HESSIAN_DARK, HESSIAN_BRIGHT, HESSIAN_SADDLE = 0, 1, 2   # pyramid.h:51-55
 
 EXPORTED_SYMBOLS = [
     "hesaff_abi_version", "hesaff_last_error", "hesaff_params_default", "hesaff_create", "hesaff_destroy",
-    "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
+    "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_detect_rgb8", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
     "hesaff_result_keypoints_device", "hesaff_set_host_output", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
     "hesaff_debug_octave_size", "hesaff_debug_plane", "hesaff_debug_patches", "hesaff_launch_count",
     "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_blur_time_ms", "hesaff_write_sift_file",
@@ -72,7 +72,7 @@ def lib():
         L.hesaff_last_error.restype = C.c_char_p
         L.hesaff_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(HessianAffineParams)] + [C.c_int] * 5
         L.hesaff_destroy.argtypes = [C.c_void_p]
-        for name in ("hesaff_detect_u8", "hesaff_detect_f32"):
+        for name in ("hesaff_detect_u8", "hesaff_detect_f32", "hesaff_detect_rgb8"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
         L.hesaff_result_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hesaff_result_total.argtypes = [C.c_void_p]
@@ -167,13 +167,14 @@ class AffineHessianDetector:
             a = np.asarray(images)
             if a.ndim == 2:
                 a = a[None]
-            assert a.ndim == 3
+            rgb = a.ndim == 4 and a.shape[3] == 3 and a.dtype == np.uint8   # [N,H,W,3] interleaved colour: gray on the GPU
+            assert a.ndim == 3 or rgb
             if a.dtype != np.uint8:
                 a = a.astype(np.float32, copy=False)
             a = np.ascontiguousarray(a)
-            n, h, w = a.shape
-            fn = lib().hesaff_detect_u8 if a.dtype == np.uint8 else lib().hesaff_detect_f32
-            rp = w * a.itemsize
+            n, h, w = a.shape[:3]
+            fn = lib().hesaff_detect_rgb8 if rgb else (lib().hesaff_detect_u8 if a.dtype == np.uint8 else lib().hesaff_detect_f32)
+            rp = w * a.itemsize * (3 if rgb else 1)
             ptr, ist = a.ctypes.data, rp * h   # C-contiguous (a[None] reports a zero stride for the new axis)
             self._keep = a
         _check(fn(self._h, C.c_void_p(ptr), n, w, h, rp, ist, on_device, C.c_void_p(stream or 0)))

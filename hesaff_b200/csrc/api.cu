@@ -480,13 +480,15 @@ static int flush_lane_output(hesaff_ctx *c, Lane &L)
    return HESAFF_OK;
 }
 
-static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int W, int H, size_t row_pitch,
+enum InFmt { IN_U8 = 0, IN_F32 = 1, IN_RGB8 = 2 };
+
+static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int W, int H, size_t row_pitch,
                        size_t img_stride, int on_device, void *stream_)
 {
    if (!c) return fail(HESAFF_ERR_INVALID, "ctx is NULL");
    if (!images || n < 0 || W < 1 || H < 1) return fail(HESAFF_ERR_INVALID, "bad image arguments");
    if (W > c->max_w || H > c->max_h) return fail(HESAFF_ERR_INVALID, "image larger than the context was created for");
-   const size_t esz = is_u8 ? 1 : 4;
+   const size_t esz = fmt == IN_U8 ? 1 : (fmt == IN_RGB8 ? 3 : 4);
    if (row_pitch < (size_t)W * esz || img_stride < row_pitch * (size_t)(H - 1) + (size_t)W * esz)
       return fail(HESAFF_ERR_INVALID, "row pitch / image stride too small");
    CK(cudaSetDevice(c->device));
@@ -562,7 +564,8 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
       // buys is the upload of chunk k+1 and the download of chunk k-1 running under the compute of chunk k.
       if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
       float *img_plane = L.arena + g.img_off;
-      if (is_u8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
+      if (fmt == IN_U8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
+      else if (fmt == IN_RGB8) ha_launch_convert_rgb8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[1], st);
 
@@ -683,13 +686,19 @@ static int detect_impl(hesaff_ctx *c, const void *images, bool is_u8, int n, int
 extern "C" int hesaff_detect_u8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
                                 size_t image_stride_bytes, int on_device, void *stream)
 {
-   return detect_impl(ctx, images, true, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+   return detect_impl(ctx, images, IN_U8, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
 }
 
 extern "C" int hesaff_detect_f32(hesaff_ctx *ctx, const float *images, int n, int width, int height, size_t row_pitch_bytes,
                                  size_t image_stride_bytes, int on_device, void *stream)
 {
-   return detect_impl(ctx, images, false, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+   return detect_impl(ctx, images, IN_F32, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+}
+
+extern "C" int hesaff_detect_rgb8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
+                                  size_t image_stride_bytes, int on_device, void *stream)
+{
+   return detect_impl(ctx, images, IN_RGB8, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
 }
 
 // ---- results -------------------------------------------------------------------------------------------

@@ -129,6 +129,8 @@ struct LaunchCounter {
 
 void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
                           cudaStream_t st, LaunchCounter &lc);
+void ha_launch_convert_rgb8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
+                            cudaStream_t st, LaunchCounter &lc);
 void ha_launch_convert_f32(const float *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
                            cudaStream_t st, LaunchCounter &lc);
 // one blur level: src plane -> dstL (+ response dstR, + decimated copy `half`), replicate border

@@ -43,6 +43,27 @@ __global__ void k_convert_f32(const float *__restrict__ src, size_t row_pitch_by
    dst[(size_t)n * arena_stride + (size_t)y * pitch + x] = s[x];
 }
 
+// 3-channel interleaved 8-bit input: gray = (float(c0) + c1 + c2) / 3.0f, the expression of hesaff.cpp:145 (the sum of
+// three bytes is exact in fp32, so the channel order does not matter; the division is IEEE, -prec-div=true)
+__global__ void k_convert_rgb8(const uint8_t *__restrict__ src, size_t row_pitch, size_t img_stride, float *__restrict__ dst,
+                               int W, int H, int pitch, unsigned long long arena_stride)
+{
+   const int x = blockIdx.x * blockDim.x + threadIdx.x;
+   const int y = blockIdx.y;
+   const int n = blockIdx.z;
+   if (x >= W) return;
+   const uint8_t *s = src + (size_t)n * img_stride + (size_t)y * row_pitch + 3 * (size_t)x;
+   dst[(size_t)n * arena_stride + (size_t)y * pitch + x] = ((float)s[0] + (float)s[1] + (float)s[2]) / 3.0f;
+}
+
+void ha_launch_convert_rgb8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
+                            cudaStream_t st, LaunchCounter &lc)
+{
+   dim3 grid((g.W + 255) / 256, g.H, n);
+   k_convert_rgb8<<<grid, 256, 0, st>>>(src, row_pitch, img_stride, dst, g.W, g.H, g.pitch[0], g.arena_stride);
+   lc.n++;
+}
+
 void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
                           cudaStream_t st, LaunchCounter &lc)
 {

@@ -107,11 +107,9 @@ int main(int argc, char **argv)
          int rc = hesaff_create(&ctx, &p, device, w, h, 1, 0);
          if (rc == HESAFF_OK) {
             if (!rgb.empty()) {
-               vector<float> image((size_t)w * h);
-               const unsigned char *in = rgb.data();   // PNM is RGB; the sum is order independent
-               for (size_t i = 0; i < image.size(); i++, in += 3) image[i] = (float(in[0]) + in[1] + in[2]) / 3.0f;
+               // colour input: the gray conversion (float(c0)+c1+c2)/3.0f of hesaff.cpp:138-148 runs on the GPU
                t1 = wallTime();
-               rc = hesaff_detect_f32(ctx, image.data(), 1, w, h, sizeof(float) * w, sizeof(float) * w * h, 0, 0);
+               rc = hesaff_detect_rgb8(ctx, rgb.data(), 1, w, h, (size_t)3 * w, (size_t)3 * w * h, 0, 0);
             } else {
                t1 = wallTime();
                rc = hesaff_detect_u8(ctx, gray.data(), 1, w, h, (size_t)w, (size_t)w * h, 0, 0);

@@ -100,6 +100,8 @@ int hesaff_destroy(hesaff_ctx *ctx);
  * `images` holds n planes, plane i at images + i*image_stride_bytes, rows row_pitch_bytes apart.
  *   hesaff_detect_u8   : 8-bit gray (what main() builds from a gray PGM: (B+G+R)/3.0f is exact, hesaff.cpp:138-148)
  *   hesaff_detect_f32  : float gray (for colour input converted by the caller with the same expression)
+ *   hesaff_detect_rgb8 : 8-bit, 3 interleaved channels (what imread hands to main(), hesaff.cpp:137); the gray
+ *                        conversion (float(c0)+c1+c2)/3.0f of hesaff.cpp:145 runs on the GPU
  * `on_device` != 0 means `images` is a device pointer on the context's GPU; otherwise it is host memory
  * (pinned memory makes the upload asynchronous).  `stream` is a cudaStream_t (NULL = the context's own
  * stream); the call returns after the work is enqueued AND the per-image counts are known on the host.
@@ -108,6 +110,8 @@ int hesaff_detect_u8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, i
                      size_t image_stride_bytes, int on_device, void *stream);
 int hesaff_detect_f32(hesaff_ctx *ctx, const float *images, int n, int width, int height, size_t row_pitch_bytes,
                       size_t image_stride_bytes, int on_device, void *stream);
+int hesaff_detect_rgb8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
+                       size_t image_stride_bytes, int on_device, void *stream);
 
 /* ---- results of the last detect call ---------------------------------------------------------- */
 /* Per image: detections (g_numberOfPoints, hesaff.cpp:68) and described keypoints (g_numberOfAffinePoints /

@@ -396,3 +396,22 @@ def test_gpu_float_formatter_is_exact_percent_g(hb):
     # values the device path does not cover are flagged, not misprinted
     assert det.formatFloats(np.float32([np.inf, np.nan, 1e19])) == ["?", "?", "?"]
     det.close()
+
+
+def test_rgb8_ingest_matches_host_gray_conversion(hb):
+    """interleaved 8-bit colour input, gray = (float(c0)+c1+c2)/3.0f (hesaff.cpp:138-148) on the GPU,
+    equals the float path fed with the host-side conversion; a gray image replicated to 3 channels equals the u8 path."""
+    rng = np.random.default_rng(3)
+    g = textured(320, 240, 71)
+    rgb = np.stack([g, np.roll(g, 3, 1), np.roll(g, 5, 0)], -1)
+    rgb = np.clip(rgb.astype(np.int32) + rng.integers(-20, 21, rgb.shape), 0, 255).astype(np.uint8)
+    gray = (rgb[..., 0].astype(np.float32) + rgb[..., 1].astype(np.float32) + rgb[..., 2].astype(np.float32)) / np.float32(3.0)
+    a = run(hb, gray)
+    b = hb.AffineHessianDetector(hb.HessianAffineParams(), 0, 320, 240, 2)
+    b.detectPyramidKeypoints(np.stack([rgb, np.repeat(g[:, :, None], 3, 2)]))
+    kb, ob = b.keys(), b.offsets()
+    assert a.keys().tobytes() == kb[ob[0]:ob[1]].tobytes()
+    c = run(hb, g)
+    assert c.keys().tobytes() == kb[ob[1]:ob[2]].tobytes()
+    for x in (a, b, c):
+        x.close()
