@@ -10,6 +10,7 @@
 //   getHessianPointType                                      pyramid.cpp:24-37
 //   octaveMap dedup                                          pyramid.cpp:189-193,226
 #include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 
 // =================================================================================================
@@ -303,110 +304,126 @@ void ha_launch_hessian(const float *src, float *dst, int W, int H, int pitch, un
 // K2a: 3x3x3 extrema -> candidate bitmask (findLevelKeypoints + isMax/isMin, pyramid.cpp:206-222,39-61)
 // One warp = 32 consecutive pixels of a row = one mask word (ballot).  Every word is written.
 // =================================================================================================
+// Up to NMS_MAXL consecutive levels per launch: the 3x3 spatial max / min of every response plane is computed once and
+// shared by the (up to three) levels whose 3x3x3 neighbourhood contains it, and every plane is read once per launch
+// instead of once per level (S = 3: 5 plane reads instead of 9, ~2.6x fewer instructions).
+#define NMS_MAXL 3
 struct NmsArgs {
-   const float *low, *cur, *high;
+   const float *plane[NMS_MAXL + 2];     // R[l0-1] .. R[l0+NL]
+   uint32_t *mask[NMS_MAXL];             // candidate bitmask of levels l0 .. l0+NL-1
    unsigned long long img_stride;
    int W, H, pitch, border, wpr;
    float posThr, negThr;
-   uint32_t *mask;
    unsigned long long mask_stride;
 };
 
-// Each warp owns a strip of 32 columns (= one mask word per row) and marches down NMS_ROWS rows keeping, per
-// response plane, the horizontal 3-max / 3-min of the two previous rows in registers: every response value is
-// loaded once per level (plus the 2 strip-edge columns), i.e. 3 x 4 B per pixel-level.
+// Each warp owns a strip of 32 columns (= one mask word per row and level) and marches down NMS_ROWS rows keeping, per
+// response plane, the horizontal 3-max / 3-min of the two previous rows in registers.
 #define NMS_ROWS 32
 #define NMS_WARPS 4
 
+template <int NL>
 __global__ void __launch_bounds__(NMS_WARPS * 32) k_nms(NmsArgs a)
 {
+   constexpr int NP = NL + 2;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const int wcol = blockIdx.x * NMS_WARPS + wid;
    if (wcol >= a.wpr) return;
    const int c = wcol * 32 + lane;
    const int cc = min(c, a.W - 1);                       // clamped column for the loads of out-of-image lanes
-   const int cl = max(cc - 1, 0), cr = min(cc + 1, a.W - 1);
+   // the strip's outer neighbour columns: lane 0 fetches column c-1, lane 31 column c+1 (one extra load instruction)
+   const int ce = lane == 0 ? max(cc - 1, 0) : min(cc + 1, a.W - 1);
+   const bool edge_lane = lane == 0 || lane == 31;
    const int r0 = blockIdx.y * NMS_ROWS;
    const int r1 = min(r0 + NMS_ROWS, a.H);
    const size_t ioff = (size_t)blockIdx.z * a.img_stride;
-   const float *planes[3] = {a.low + ioff, a.cur + ioff, a.high + ioff};
-   uint32_t *mrow = a.mask + (size_t)blockIdx.z * a.mask_stride + wcol;
+   const size_t moff = (size_t)blockIdx.z * a.mask_stride + wcol;
    const bool col_ok = c >= a.border && c < a.W - a.border;
 
-   float hmax[3][2], hmin[3][2], vcur[2];
+   float hmax[NP][2], hmin[NP][2], vcur[NL][2];
 #pragma unroll
-   for (int p = 0; p < 3; p++) { hmax[p][0] = hmax[p][1] = 0.f; hmin[p][0] = hmin[p][1] = 0.f; }
-   vcur[0] = vcur[1] = 0.f;
+   for (int p = 0; p < NP; p++) { hmax[p][0] = hmax[p][1] = 0.f; hmin[p][0] = hmin[p][1] = 0.f; }
+#pragma unroll
+   for (int l = 0; l < NL; l++) vcur[l][0] = vcur[l][1] = 0.f;
 
-   // software pipeline: the loads of row rr+1 are in flight while row rr is reduced (the shuffles below would
-   // otherwise expose the full memory latency once per row)
-   float nv[3], nl[3], nr[3];
+   // software pipeline: the loads of row rr+1 are in flight while row rr is reduced
+   float nv[NP], ne[NP];
    {
       const int rl = min(max(r0 - 1, 0), a.H - 1);
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
-         const float *row = planes[p] + (size_t)rl * a.pitch;
-         nv[p] = __ldg(row + cc); nl[p] = __ldg(row + cl); nr[p] = __ldg(row + cr);
+      for (int p = 0; p < NP; p++) {
+         const float *row = a.plane[p] + ioff + (size_t)rl * a.pitch;
+         nv[p] = __ldg(row + cc);
+         ne[p] = edge_lane ? __ldg(row + ce) : 0.f;
       }
    }
    for (int rr = r0 - 1; rr <= r1; rr++) {
-      float v[3], le[3], re[3];
+      float v[NP], e[NP];
 #pragma unroll
-      for (int p = 0; p < 3; p++) { v[p] = nv[p]; le[p] = nl[p]; re[p] = nr[p]; }
+      for (int p = 0; p < NP; p++) { v[p] = nv[p]; e[p] = ne[p]; }
       if (rr < r1) {
          const int rl = min(max(rr + 1, 0), a.H - 1);
 #pragma unroll
-         for (int p = 0; p < 3; p++) {
-            const float *row = planes[p] + (size_t)rl * a.pitch;
-            nv[p] = __ldg(row + cc); nl[p] = __ldg(row + cl); nr[p] = __ldg(row + cr);
+         for (int p = 0; p < NP; p++) {
+            const float *row = a.plane[p] + ioff + (size_t)rl * a.pitch;
+            nv[p] = __ldg(row + cc);
+            ne[p] = edge_lane ? __ldg(row + ce) : 0.f;
          }
       }
-      float nmax[3], nmin[3];
+      float nmax[NP], nmin[NP];
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
+      for (int p = 0; p < NP; p++) {
          float l = __shfl_up_sync(0xffffffffu, v[p], 1);
          float r = __shfl_down_sync(0xffffffffu, v[p], 1);
-         if (lane == 0) l = le[p];
-         if (lane == 31) r = re[p];
+         if (lane == 0) l = e[p];
+         if (lane == 31) r = e[p];
          nmax[p] = fmaxf(fmaxf(l, r), v[p]);
          nmin[p] = fminf(fminf(l, r), v[p]);
       }
-      const float vnew = v[1];
       if (rr >= r0 + 1) {
          const int ro = rr - 1;   // output row: rows ro-1 (age 0), ro (age 1), ro+1 (new) are available
-         float M = fmaxf(fmaxf(hmax[0][0], hmax[0][1]), nmax[0]);
-         float m = fminf(fminf(hmin[0][0], hmin[0][1]), nmin[0]);
+         float pmax[NP], pmin[NP];   // 3x3 max / min of every plane around (ro, c)
 #pragma unroll
-         for (int p = 1; p < 3; p++) {
-            M = fmaxf(M, fmaxf(fmaxf(hmax[p][0], hmax[p][1]), nmax[p]));
-            m = fminf(m, fminf(fminf(hmin[p][0], hmin[p][1]), nmin[p]));
+         for (int p = 0; p < NP; p++) {
+            pmax[p] = fmaxf(fmaxf(hmax[p][0], hmax[p][1]), nmax[p]);
+            pmin[p] = fminf(fminf(hmin[p][0], hmin[p][1]), nmin[p]);
          }
-         const float val = vcur[1];
-         // findLevelKeypoints (pyramid.cpp:215-217): val > positiveThreshold and no neighbour above it (ties pass),
-         // or val < negativeThreshold and no neighbour below it
-         const bool cand = col_ok && ro >= a.border && ro < a.H - a.border &&
-                           ((val > a.posThr && !(M > val)) || (val < a.negThr && !(m < val)));
-         const unsigned word = __ballot_sync(0xffffffffu, cand);
-         if (lane == 0) mrow[(size_t)ro * a.wpr] = word;
+         const bool pos_ok = col_ok && ro >= a.border && ro < a.H - a.border;
+#pragma unroll
+         for (int l = 0; l < NL; l++) {
+            const float M = fmaxf(fmaxf(pmax[l], pmax[l + 1]), pmax[l + 2]);
+            const float m = fminf(fminf(pmin[l], pmin[l + 1]), pmin[l + 2]);
+            const float val = vcur[l][1];
+            // findLevelKeypoints (pyramid.cpp:215-217): val > positiveThreshold and no neighbour above it (ties pass),
+            // or val < negativeThreshold and no neighbour below it
+            const bool cand = pos_ok && ((val > a.posThr && !(M > val)) || (val < a.negThr && !(m < val)));
+            const unsigned word = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0) a.mask[l][moff + (size_t)ro * a.wpr] = word;
+         }
       }
 #pragma unroll
-      for (int p = 0; p < 3; p++) { hmax[p][0] = hmax[p][1]; hmax[p][1] = nmax[p]; hmin[p][0] = hmin[p][1]; hmin[p][1] = nmin[p]; }
-      vcur[0] = vcur[1]; vcur[1] = vnew;
+      for (int p = 0; p < NP; p++) { hmax[p][0] = hmax[p][1]; hmax[p][1] = nmax[p]; hmin[p][0] = hmin[p][1]; hmin[p][1] = nmin[p]; }
+#pragma unroll
+      for (int l = 0; l < NL; l++) { vcur[l][0] = vcur[l][1]; vcur[l][1] = v[l + 1]; }
    }
 }
 
 void ha_launch_nms(const float *arena, const Geom &g, const Geom *, uint32_t *mask, int n, cudaStream_t st, LaunchCounter &lc)
 {
    for (int o = 0; o < g.nOct; o++)
-      for (int l = 1; l <= g.S; l++) {
+      for (int l0 = 1; l0 <= g.S; l0 += NMS_MAXL) {
+         const int nl = std::min(NMS_MAXL, g.S - l0 + 1);
          NmsArgs a;
-         a.low = arena + g.R_off[o][l - 1]; a.cur = arena + g.R_off[o][l]; a.high = arena + g.R_off[o][l + 1];
+         for (int p = 0; p < nl + 2; p++) a.plane[p] = arena + g.R_off[o][l0 - 1 + p];
+         for (int l = 0; l < nl; l++) a.mask[l] = mask + g.mask_off[o][l0 + l];
          a.img_stride = g.arena_stride;
          a.W = g.w[o]; a.H = g.h[o]; a.pitch = g.pitch[o]; a.border = g.border; a.wpr = g.wpr[o];
          a.posThr = g.positiveThreshold; a.negThr = g.negativeThreshold;
-         a.mask = mask + g.mask_off[o][l]; a.mask_stride = g.mask_stride;
+         a.mask_stride = g.mask_stride;
          dim3 grid((g.wpr[o] + NMS_WARPS - 1) / NMS_WARPS, (g.h[o] + NMS_ROWS - 1) / NMS_ROWS, n);
-         k_nms<<<grid, NMS_WARPS * 32, 0, st>>>(a);
+         if (nl == 3) k_nms<3><<<grid, NMS_WARPS * 32, 0, st>>>(a);
+         else if (nl == 2) k_nms<2><<<grid, NMS_WARPS * 32, 0, st>>>(a);
+         else k_nms<1><<<grid, NMS_WARPS * 32, 0, st>>>(a);
          lc.n++;
       }
 }
