@@ -105,7 +105,7 @@ __device__ __forceinline__ u64 row_pair(const float (&v)[NV], int o, const float
 #undef HA_P
 }
 
-template <int N, int OH, int NT, int MINB, bool SHIFT>
+template <int N, int OH, int NT, int MINB, bool SHIFT, bool SHFL_EDGES>
 __global__ void __launch_bounds__(NT, MINB)
 k_blur_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Blur3Args a, const __grid_constant__ Taps taps)
 {
@@ -173,10 +173,25 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Blu
    for (int my = warp; my < IH; my += NWARPS) {
       const float *p = sIN + my * BW + 4 * lane;
       float v[4 * NLD];
+      // When only the last float of the first quad / the first float of the last quad is needed (D = 3: 11 and 19 taps),
+      // it is the neighbouring lane's: one shuffle instead of a 4-way bank-conflicting scalar load (4 wavefronts).
+      constexpr int LASTF = D + N + 2;                                   // last float index read
+      constexpr bool HEAD1 = SHFL_EDGES && D == 3;
+      constexpr bool TAIL1 = SHFL_EDGES && (LASTF % 4 == 0) && (LASTF / 4 == NLD - 1) && NLD >= 3;
 #pragma unroll
-      for (int i = 0; i < NLD; i++) {
+      for (int i = (HEAD1 ? 1 : 0); i < (TAIL1 ? NLD - 1 : NLD); i++) {
          const float4 q = *reinterpret_cast<const float4 *>(p + 4 * i);
          v[4 * i + 0] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+      if (HEAD1) {
+         v[0] = v[1] = v[2] = 0.f;
+         v[3] = __shfl_up_sync(0xffffffffu, v[7], 1);
+         if (lane == 0) v[3] = p[3];
+      }
+      if (TAIL1) {
+         v[LASTF] = __shfl_down_sync(0xffffffffu, v[LASTF - 4], 1);
+         v[LASTF + 1] = v[LASTF + 2] = v[LASTF + 3] = 0.f;
+         if (lane == 31) v[LASTF] = p[LASTF];
       }
       const u64 o01 = row_pair<N>(v, D, taps.k);
       const u64 o23 = row_pair<N>(v, D + 2, taps.k);
@@ -289,7 +304,7 @@ static EncodeTiledFn get_encode()
    return fn;
 }
 
-template <int N, int OH, int NT, int MINB, bool SHIFT>
+template <int N, int OH, int NT, int MINB, bool SHIFT, bool SHFL_EDGES>
 static int launch_tma_n(const float *src, const Blur3Args &a, const Taps &taps, int n, cudaStream_t st)
 {
    using namespace blur3;
@@ -306,12 +321,12 @@ static int launch_tma_n(const float *src, const Blur3Args &a, const Taps &taps, 
       return -1;
    static bool attr_set = false;   // one static per instantiation
    if (!attr_set) {
-      if (cudaFuncSetAttribute(k_blur_tma<N, OH, NT, MINB, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+      if (cudaFuncSetAttribute(k_blur_tma<N, OH, NT, MINB, SHIFT, SHFL_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
          return -1;
       attr_set = true;
    }
    dim3 grid((a.W + TW - 1) / TW, (a.H + C::TH - 1) / C::TH, n);
-   k_blur_tma<N, OH, NT, MINB, SHIFT><<<grid, NT, C::SMEM, st>>>(tm, a, taps);
+   k_blur_tma<N, OH, NT, MINB, SHIFT, SHFL_EDGES><<<grid, NT, C::SMEM, st>>>(tm, a, taps);
    return 0;
 }
 
@@ -321,7 +336,7 @@ static int launch_tma_n(const float *src, const Blur3Args &a, const Taps &taps, 
 
 // Returns 0 when the TMA kernel was launched, -1 when this shape/tap count is not covered (caller falls back).
 // variant: 0 = default configuration; bench builds (HA_BLUR_VARIANTS) accept oh | (threads/32 << 8) | (min CTAs/SM << 16) |
-// (shift << 25).
+// (shift << 25) | (shuffled edge floats << 26).
 int ha_launch_blur_tma(const float *src, float *dstL, float *dstR, float *half, int W, int H, int pitch, int hW, int hH,
                        int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
                        int variant)
@@ -333,10 +348,10 @@ int ha_launch_blur_tma(const float *src, float *dstL, float *dstR, float *half, 
    a.norm2 = norm * norm;   // pyramid.cpp:76
 #if HA_BLUR_VARIANTS
    if (variant) {
-#define HA_V(N, OHV, NW, MINB, SH) \
-      if (taps.n == N && variant == (OHV | (NW << 8) | (MINB << 16) | (SH << 25))) \
-         return launch_tma_n<N, OHV, NW * 32, MINB, SH != 0>(src, a, taps, n, st);
-#define HA_VN(N) HA_V(N, 40, 8, 4, 1) HA_V(N, 40, 8, 4, 0) HA_V(N, 48, 8, 3, 1) HA_V(N, 56, 8, 3, 1) HA_V(N, 56, 8, 2, 1)
+#define HA_V(N, OHV, NW, MINB, SH, SE) \
+      if (taps.n == N && variant == (OHV | (NW << 8) | (MINB << 16) | (SH << 25) | (SE << 26))) \
+         return launch_tma_n<N, OHV, NW * 32, MINB, SH != 0, SE != 0>(src, a, taps, n, st);
+#define HA_VN(N) HA_V(N, 40, 8, 4, 1, 0) HA_V(N, 40, 8, 4, 1, 1) HA_V(N, 48, 8, 3, 1, 1) HA_V(N, 56, 8, 3, 1, 1) HA_V(N, 56, 8, 2, 1, 1) HA_V(N, 56, 8, 2, 1, 0)
       HA_VN(9) HA_VN(11) HA_VN(13) HA_VN(15)
 #undef HA_VN
 #undef HA_V
@@ -347,8 +362,8 @@ int ha_launch_blur_tma(const float *src, float *dstL, float *dstR, float *half, 
    // measured on B200 (tools/blur_bench.cu, 32 x 1080p): up to 13 taps 38-row tiles with 4 CTAs/SM are fastest, from 15
    // taps on the halo makes 54-row tiles (2 CTAs/SM, more registers) win
    switch (taps.n) {
-#define HA_CASE(N) case N: return launch_tma_n<N, 40, 256, 4, true>(src, a, taps, n, st);
-#define HA_CASE_TALL(N) case N: return launch_tma_n<N, 56, 256, 2, true>(src, a, taps, n, st);
+#define HA_CASE(N) case N: return launch_tma_n<N, 40, 256, 4, true, true>(src, a, taps, n, st);
+#define HA_CASE_TALL(N) case N: return launch_tma_n<N, 56, 256, 2, true, true>(src, a, taps, n, st);
       HA_CASE(1) HA_CASE(3) HA_CASE(5) HA_CASE(7) HA_CASE(9) HA_CASE(11) HA_CASE(13)
       HA_CASE_TALL(15) HA_CASE_TALL(17) HA_CASE_TALL(19) HA_CASE_TALL(21)
 #undef HA_CASE

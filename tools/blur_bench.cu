@@ -86,10 +86,11 @@ int main(int argc, char **argv)
          CKB(cudaMemcpy(hHr.data(), Hr, total * 4, cudaMemcpyDeviceToHost));
       }
       struct V { const char *name; int kind; int variant; };
-#define VV(oh, nw, minb, sh) (oh | (nw << 8) | (minb << 16) | (sh << 25))
+#define VV(oh, nw, minb, sh, se) (oh | (nw << 8) | (minb << 16) | (sh << 25) | (se << 26))
       std::vector<V> vs = {{"v1 k_blur (no TMA)", 1, 0}, {"v2 k_blur_v2 (r1b)", 2, 0}, {"v3 default", 3, 0},
-                           {"v3 oh40 x4", 3, VV(40, 8, 4, 1)}, {"v3 oh40 x4 noshift", 3, VV(40, 8, 4, 0)},
-                           {"v3 oh48 x3", 3, VV(48, 8, 3, 1)}, {"v3 oh56 x3", 3, VV(56, 8, 3, 1)}, {"v3 oh56 x2", 3, VV(56, 8, 2, 1)}};
+                           {"v3 oh40 x4 noshfl", 3, VV(40, 8, 4, 1, 0)}, {"v3 oh40 x4", 3, VV(40, 8, 4, 1, 1)},
+                           {"v3 oh48 x3", 3, VV(48, 8, 3, 1, 1)}, {"v3 oh56 x3", 3, VV(56, 8, 3, 1, 1)}, {"v3 oh56 x2", 3, VV(56, 8, 2, 1, 1)},
+                           {"v3 oh56 x2 noshfl", 3, VV(56, 8, 2, 1, 0)}};
       for (const V &v : vs) {
          if (filter && !strstr(v.name, filter)) continue;
          auto run = [&]() -> int {
