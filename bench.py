@@ -143,7 +143,7 @@ def _cpu_worker(args):
 
 def ncu_traffic():
     """DRAM bytes (read+write) of one octave-0 k_blur_tma launch from the committed `ncu --set full` capture
-    (profiles/r1b_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
+    (profiles/r1c_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
     path = os.path.join(ROOT, "profiles", "r1b_k_blur_tma_ncu.txt")
     try:
         rd = wr = None
@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="batch1024_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
-    ap.add_argument("--cpu-images", type=int, default=0, help="CPU sample size (default: one image per host core, <= 128)")
+    ap.add_argument("--cpu-images", type=int, default=0, help="CPU sample size (default: three images per host core, <= 192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -230,7 +230,7 @@ def main():
             return 0
         import torch
         from tools.gen_textured import textured
-        n_cpu = args.cpu_images or min(host_cores, 128)
+        n_cpu = args.cpu_images or min(3 * host_cores, 192)   # ~10-20 s of host work per step
         if torch.cuda.is_available():
             imgs = synth_textured_gpu(torch, n_cpu, H, W, 1234, "cuda:0").cpu().numpy()
         else:
@@ -387,13 +387,13 @@ def main():
                          "algorithmic_bytes_per_image": blur_bytes, "survey_bytes_per_image_incl_nms": survey_bytes,
                          "traffic": ncu_traffic()[0],
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE octave-0 k_blur_tma<11> launch over "
-                                         "32 x 1920x1080 (ncu --set full, profiles/r1b_k_blur_tma_ncu.txt); algorithmic bytes of "
+                                         "32 x 1920x1080 (ncu --set full, profiles/r1c_k_blur_tma_ncu.txt); algorithmic bytes of "
                                          "that launch: %.0f" % (ncu_traffic()[1] or 0)},
             "clocks": clk,
             "host_cores": host_cores, "host_threads": host_threads,
         }
         if not args.no_cpu_baseline:
-            n_cpu = args.cpu_images or min(host_cores, 128, batch)
+            n_cpu = args.cpu_images or min(3 * host_cores, 192, batch)   # ~10-20 s of host work
             sample = images[:n_cpu].cpu().numpy()
             r = cpu_reference_run(sample, over, host_cores)
             cpu_v = r["mpix"] / r["wall_s"]
