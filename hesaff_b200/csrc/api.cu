@@ -200,6 +200,32 @@ static int build_tables(hesaff_ctx *c)
    int rc;
    if ((rc = upload(c, m19, &c->tables.smm_mask))) return rc;
    if ((rc = upload(c, m41, &c->tables.sift_mask))) return rc;
+   {  // pixel lists of the SIFT passes (see Tables)
+      std::vector<uint2> disc;
+      std::vector<uint32_t> outside, need, all;
+      std::vector<char> needed(HA_PATCH_PX, 0);
+      for (int r = 0; r < HA_PATCH; r++)
+         for (int q = 0; q < HA_PATCH; q++) {
+            const int t = r * HA_PATCH + q;
+            if (m41[t] > 0) {
+               uint32_t bits;
+               memcpy(&bits, &m41[t], 4);
+               disc.push_back(make_uint2((unsigned)t, bits));
+               if (r < 1 || q < 1 || r > HA_PATCH - 2 || q > HA_PATCH - 2) return fail(HESAFF_ERR_INVALID, "SIFT mask touches the patch border");
+               needed[t] = needed[t - 1] = needed[t + 1] = needed[t - HA_PATCH] = needed[t + HA_PATCH] = 1;
+            } else outside.push_back((uint32_t)t);
+         }
+      for (int t = 0; t < HA_PATCH_PX; t++) {
+         const uint32_t w = (uint32_t)t | ((uint32_t)(t / HA_PATCH) << 16) | ((uint32_t)(t % HA_PATCH) << 24);
+         all.push_back(w);
+         if (needed[t]) need.push_back(w);
+      }
+      if (disc.size() != HA_SIFT_ND || need.size() != HA_SIFT_NN) return fail(HESAFF_ERR_INVALID, "SIFT mask geometry differs from HA_SIFT_ND / HA_SIFT_NN");
+      if ((rc = upload(c, disc, &c->tables.sift_disc))) return rc;
+      if ((rc = upload(c, outside, &c->tables.sift_out))) return rc;
+      if ((rc = upload(c, need, &c->tables.sift_need))) return rc;
+      if ((rc = upload(c, all, &c->tables.sift_all))) return rc;
+   }
    // per-patch blur kernels, indexed by m = (P0-1)/2.  interpolateCheckBorders (helpers.cpp:191-207) only accepts a
    // keypoint whose 41x41 footprint (+-20*its*A, det A = 1) lies inside the image: 40*its*a11 < W and 40*its*a22 < H,
    // hence its < sqrt(W*H)/40 and P0 = 41*its < 1.025*sqrt(W*H).

@@ -13,6 +13,8 @@
 #define HA_MAX_TAPS 33         // pyramid blur taps passed by value to the kernels
 #define HA_PATCH 41            // SIFT patch side (siftdesc.h:30, affine.h:42)
 #define HA_PATCH_PX (HA_PATCH * HA_PATCH)
+#define HA_SIFT_ND 1245         // pixels with a non-zero SIFT mask weight: (r-20)^2 + (c-20)^2 < 400 (helpers.cpp:131-147)
+#define HA_SIFT_NN 1361         // those pixels and their 4-neighbours = every patch pixel the descriptor can depend on
 #define HA_SMM 19              // SMM window side (affine.h:43)
 #define HA_SMM_PX (HA_SMM * HA_SMM)
 
@@ -95,6 +97,11 @@ struct Bins {
 struct Tables {
    const float *smm_mask;     // 19x19, computeGaussMask helpers.cpp:104-129
    const float *sift_mask;    // 41x41, computeCircularGaussMask helpers.cpp:131-147
+   // The mask is zero outside a disc that never touches the patch border, so the SIFT passes run over lists:
+   const uint2 *sift_disc;    // [HA_SIFT_ND] {patch index r*41+c, mask weight bits} of the pixels inside the disc, raster order
+   const uint32_t *sift_out;  // [41*41 - HA_SIFT_ND] patch indices outside the disc
+   const uint32_t *sift_need; // [HA_SIFT_NN] index | row << 16 | col << 24 of the disc pixels and their 4-neighbours
+   const uint32_t *sift_all;  // [41*41] the same packing for every pixel (patch dumps)
    // per-patch blur kernels indexed by m = (P0-1)/2 (P0 = 2*int(mrScale)+1): taps n and offset of the
    // R+1 half kernel k[R..n-1] in `pk`
    const int *pk_n;
