@@ -415,3 +415,29 @@ def test_rgb8_ingest_matches_host_gray_conversion(hb):
     assert c.keys().tobytes() == kb[ob[1]:ob[2]].tobytes()
     for x in (a, b, c):
         x.close()
+
+
+def test_device_records_and_nccl_keypoint_gather(hb):
+    """the records stay on the GPU (zero-copy view of the library's buffer) and go through the
+    variable-size all-gather over nccl (world size 1 here; two ranks are covered by the gloo test in test_host.py)."""
+    import torch
+    import torch.distributed as dist
+    from hesaff_b200 import shard
+    imgs = np.stack([textured(320, 240, 81), textured(320, 240, 82), textured(320, 240, 83)])
+    det = run(hb, imgs)
+    keys = det.keys()
+    dev = torch.device("cuda:0")
+    rec = shard.device_records(torch, det, dev)
+    assert rec.data_ptr() == det.keys_device_ptr() and tuple(rec.shape) == (len(keys), 164)
+    assert rec.cpu().numpy().tobytes() == keys.tobytes()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29700 + os.getpid() % 200))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        counts = shard.all_gather_counts(dist, torch, np.stack([det.n_detected, det.n_described], 1), dev)
+        assert np.array_equal(counts[:, 1], det.n_described)
+        got = shard.all_gather_keypoints(dist, torch, rec, counts, shard.partition(3, 1), dev)
+        assert got.cpu().numpy().tobytes() == keys.tobytes()
+    finally:
+        dist.destroy_process_group()
+    det.close()

@@ -100,6 +100,20 @@ g = shard.all_gather_counts(dist, torch, mine, "cpu")
 assert g.shape == (n_total, 2) and np.array_equal(g, all_counts), (rank, g)
 off = shard.global_offsets(g)
 assert off[-1] == all_counts[:, 1].sum() and off[starts[1]] == all_counts[:starts[1], 1].sum()
+# the step after the path: variable-size all-gather of the Keypoint records (SURVEY 8(f) rank 3)
+from hesaff_b200 import KEYPOINT_DTYPE
+recs = np.zeros(int(off[-1]), KEYPOINT_DTYPE)
+recs["x"] = np.arange(len(recs)); recs["type"] = 7; recs["desc"] = (np.arange(len(recs)) % 251)[:, None]
+lo, hi = off[starts[rank]], off[starts[rank + 1]]
+got = shard.all_gather_keypoints(dist, torch, recs[lo:hi], g, starts, "cpu")
+assert tuple(got.shape) == (len(recs), 164)
+back = got.numpy().reshape(-1).view(KEYPOINT_DTYPE)
+assert back.tobytes() == recs.tobytes(), rank
+try:
+    shard.all_gather_keypoints(dist, torch, recs[lo:hi][:-1], g, starts, "cpu")
+    raise SystemExit("size mismatch not detected")
+except ValueError:
+    pass
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
