@@ -38,11 +38,12 @@ struct Lane {
    Cand cand;
    uint32_t *det_off, *desc_off;   // cand_cap+1 each
    Bins bins;
-   int *counters;              // [0] affine work, [1..3] describe work
+   int *counters;              // [0] affine work, [1..4] describe work (one queue per bin)
    float *scratch;
    cudaEvent_t ev[8];
    std::vector<cudaEvent_t> blur_ev;   // profiling: event pairs around every k_blur launch
    cudaEvent_t done;           // recorded after the chunk's k_add_total
+   cudaEvent_t front_done;     // recorded after the chunk's affine-shape kernel (end of the front end)
    uint32_t *h_total;          // pinned: [0] described keypoints of the last chunk on this lane, [1] base offset
    int pending_chunk;          // chunk index whose results are not yet copied to the host output (-1: none)
 };
@@ -323,6 +324,7 @@ static int alloc_lane(hesaff_ctx *c, Lane &L, const Geom &g)
    CK(cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming));
    for (int i = 0; i < 8; i++) CK(cudaEventCreate(&L.ev[i]));
    CK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&L.front_done, cudaEventDisableTiming));
    CK(cudaMallocHost((void **)&L.h_total, 4 * sizeof(uint32_t)));
    const int chunk = c->chunk;
    if ((rc = dmalloc(&L.arena, g.arena_stride * chunk))) return rc;
@@ -339,7 +341,7 @@ static int alloc_lane(hesaff_ctx *c, Lane &L, const Geom &g)
        (rc = dmalloc(&L.cand.iters, cc)) || (rc = dmalloc(&L.cand.desc, cc * 128)))
       return rc;
    if ((rc = dmalloc(&L.det_off, cc + 2)) || (rc = dmalloc(&L.desc_off, cc + 2))) return rc;
-   for (int b = 0; b < 3; b++)
+   for (int b = 0; b < 4; b++)
       if ((rc = dmalloc(&L.bins.list[b], cc))) return rc;
    if ((rc = dmalloc(&L.bins.count, 4))) return rc;
    if ((rc = dmalloc(&L.counters, 8))) return rc;
@@ -352,10 +354,11 @@ static void free_lane(Lane &L)
    if (L.stream) cudaStreamSynchronize(L.stream);
    void *ptrs[] = {L.arena, L.stage_u8, L.mask, L.woff, L.scan_tmp, L.map, L.cand.key, L.cand.x, L.cand.y, L.cand.s,
                    L.cand.response, L.cand.cell, L.cand.type, L.cand.flags, L.cand.U, L.cand.A, L.cand.iters, L.cand.desc,
-                   L.det_off, L.desc_off, L.bins.list[0], L.bins.list[1], L.bins.list[2], L.bins.count, L.counters, L.scratch};
+                   L.det_off, L.desc_off, L.bins.list[0], L.bins.list[1], L.bins.list[2], L.bins.list[3], L.bins.count, L.counters, L.scratch};
    for (void *p : ptrs) if (p) cudaFree(p);
    for (int i = 0; i < 8; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
    if (L.done) cudaEventDestroy(L.done);
+   if (L.front_done) cudaEventDestroy(L.front_done);
    if (L.ev_fork) cudaEventDestroy(L.ev_fork);
    if (L.ev_join) cudaEventDestroy(L.ev_join);
    if (L.aux) cudaStreamDestroy(L.aux);
@@ -560,7 +563,11 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       c->lane[l].pending_chunk = -1;
       CK(cudaStreamWaitEvent(c->lane[l].stream, c->ev_start, 0));
    }
-   cudaEvent_t prev_done = nullptr;
+   cudaEvent_t prev_done = nullptr, prev_front = nullptr;
+   // (HESAFF_OVERLAP=0 turns this off) the front end (pyramid .. affine shape) of chunk k+1 may run under the describe stage of chunk k
+   // (front ends stay in order among themselves, and so do the describe + compaction stages)
+   static const bool overlap_front = !getenv("HESAFF_OVERLAP") || atoi(getenv("HESAFF_OVERLAP")) > 0;
+   const bool overlap = overlap_front && !c->profiling;
 
    for (int start = 0, k = 0; start < n; start += c->chunk, k++) {
       const int cn = std::min(c->chunk, n - start);
@@ -588,7 +595,8 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       // Compute of consecutive chunks is serialised (the describe stage already fills the SMs with its own
       // side-by-side kernels; a second lane's kernels only disturb that packing -- measured); what the second lane
       // buys is the upload of chunk k+1 and the download of chunk k-1 running under the compute of chunk k.
-      if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
+      if (overlap) { if (prev_front) CK(cudaStreamWaitEvent(st, prev_front, 0)); }
+      else if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
       float *img_plane = L.arena + g.img_off;
       if (fmt == IN_U8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else if (fmt == IN_RGB8) ha_launch_convert_rgb8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
@@ -644,11 +652,16 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       if (c->profiling) cudaEventRecord(L.ev[3], st);
 
       // ---- stage 3: affine shape ---------------------------------------------------------------------
-      CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 4, st));
+      CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 5, st));
       CK(cudaMemsetAsync(L.bins.count, 0, sizeof(int) * 4, st));
       ha_launch_affine(L.arena, c->d_geom, c->tables, L.cand, d_count, c->cand_cap, L.map, c->d_ndet + start, L.bins,
                        L.counters, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[4], st);
+      if (overlap) {
+         CK(cudaEventRecord(L.front_done, st));
+         prev_front = L.front_done;
+         if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
+      }
 
       // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
       ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
@@ -838,7 +851,7 @@ extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, s
    int rc;
    if ((rc = dmalloc(&d, (size_t)c->total_desc * HA_PATCH_PX))) return rc;
    Lane &L = c->lane[0];
-   CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 3, L.stream));
+   CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 4, L.stream));
    ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
                       c->large_ctas, c->maxP, d, normalized, L.desc_off, L.stream, c->lc);
    CK(cudaStreamSynchronize(L.stream));

@@ -20,7 +20,8 @@
 
 #define HA_MAX_PATCH_R 519     // largest half-width of a per-patch blur kernel (shared-memory table)
 
-#define HA_BIN_SMALL_MAXP 47   // patch+SIFT kernel bins by source-patch side P
+#define HA_BIN_TINY_MAXP 39    // patch+SIFT kernel bins by source-patch side P
+#define HA_BIN_SMALL_MAXP 47
 #define HA_BIN_MEDIUM_MAXP 95
 
 struct Taps {
@@ -89,8 +90,8 @@ struct Cand {
 
 // Work lists for the patch+SIFT kernel, binned by source patch side.
 struct Bins {
-   int *list[3];
-   int *count;                // [3]
+   int *list[4];              // [0] SMALL, [1] MEDIUM, [2] LARGE, [3] TINY
+   int *count;                // [4]
 };
 
 // Precomputed constant tables (host, glibc libm => bit-identical to the oracle), in device memory.
