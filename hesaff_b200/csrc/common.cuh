@@ -22,6 +22,7 @@
 
 #define HA_BIN_TINY_MAXP 39    // patch+SIFT kernel bins by source-patch side P
 #define HA_BIN_SMALL_MAXP 47
+#define HA_BIN_MID_MAXP 63
 #define HA_BIN_MEDIUM_MAXP 95
 
 struct Taps {
@@ -90,8 +91,8 @@ struct Cand {
 
 // Work lists for the patch+SIFT kernel, binned by source patch side.
 struct Bins {
-   int *list[4];              // [0] SMALL, [1] MEDIUM, [2] LARGE, [3] TINY
-   int *count;                // [4]
+   int *list[5];              // [0] SMALL, [1] MEDIUM, [2] LARGE, [3] TINY, [4] MID
+   int *count;                // [5]
 };
 
 // Precomputed constant tables (host, glibc libm => bit-identical to the oracle), in device memory.
