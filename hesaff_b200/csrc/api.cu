@@ -38,7 +38,7 @@ struct Lane {
    Cand cand;
    uint32_t *det_off, *desc_off;   // cand_cap+1 each
    Bins bins;
-   int *counters;              // [0] affine work, [1..5] describe work (one queue per bin)
+   int *counters;              // [0] affine work, [1..6] describe work (one queue per bin)
    float *scratch;
    cudaEvent_t ev[8];
    std::vector<cudaEvent_t> blur_ev;   // profiling: event pairs around every k_blur launch
@@ -341,7 +341,7 @@ static int alloc_lane(hesaff_ctx *c, Lane &L, const Geom &g)
        (rc = dmalloc(&L.cand.iters, cc)) || (rc = dmalloc(&L.cand.desc, cc * 128)))
       return rc;
    if ((rc = dmalloc(&L.det_off, cc + 2)) || (rc = dmalloc(&L.desc_off, cc + 2))) return rc;
-   for (int b = 0; b < 5; b++)
+   for (int b = 0; b < 6; b++)
       if ((rc = dmalloc(&L.bins.list[b], cc))) return rc;
    if ((rc = dmalloc(&L.bins.count, 8))) return rc;
    if ((rc = dmalloc(&L.counters, 8))) return rc;
@@ -354,7 +354,7 @@ static void free_lane(Lane &L)
    if (L.stream) cudaStreamSynchronize(L.stream);
    void *ptrs[] = {L.arena, L.stage_u8, L.mask, L.woff, L.scan_tmp, L.map, L.cand.key, L.cand.x, L.cand.y, L.cand.s,
                    L.cand.response, L.cand.cell, L.cand.type, L.cand.flags, L.cand.U, L.cand.A, L.cand.iters, L.cand.desc,
-                   L.det_off, L.desc_off, L.bins.list[0], L.bins.list[1], L.bins.list[2], L.bins.list[3], L.bins.list[4], L.bins.count, L.counters, L.scratch};
+                   L.det_off, L.desc_off, L.bins.list[0], L.bins.list[1], L.bins.list[2], L.bins.list[3], L.bins.list[4], L.bins.list[5], L.bins.count, L.counters, L.scratch};
    for (void *p : ptrs) if (p) cudaFree(p);
    for (int i = 0; i < 8; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
    if (L.done) cudaEventDestroy(L.done);
@@ -652,8 +652,8 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       if (c->profiling) cudaEventRecord(L.ev[3], st);
 
       // ---- stage 3: affine shape ---------------------------------------------------------------------
-      CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 6, st));
-      CK(cudaMemsetAsync(L.bins.count, 0, sizeof(int) * 5, st));
+      CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 7, st));
+      CK(cudaMemsetAsync(L.bins.count, 0, sizeof(int) * 6, st));
       ha_launch_affine(L.arena, c->d_geom, c->tables, L.cand, d_count, c->cand_cap, L.map, c->d_ndet + start, L.bins,
                        L.counters, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[4], st);
@@ -851,7 +851,7 @@ extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, s
    int rc;
    if ((rc = dmalloc(&d, (size_t)c->total_desc * HA_PATCH_PX))) return rc;
    Lane &L = c->lane[0];
-   CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 5, L.stream));
+   CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 6, L.stream));
    ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
                       c->large_ctas, c->maxP, d, normalized, L.desc_off, L.stream, c->lc);
    CK(cudaStreamSynchronize(L.stream));

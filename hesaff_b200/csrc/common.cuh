@@ -23,6 +23,7 @@
 #define HA_BIN_TINY_MAXP 39    // patch+SIFT kernel bins by source-patch side P
 #define HA_BIN_SMALL_MAXP 47
 #define HA_BIN_MID_MAXP 63
+#define HA_BIN_MID2_MAXP 79
 #define HA_BIN_MEDIUM_MAXP 95
 
 struct Taps {
@@ -91,8 +92,8 @@ struct Cand {
 
 // Work lists for the patch+SIFT kernel, binned by source patch side.
 struct Bins {
-   int *list[5];              // [0] SMALL, [1] MEDIUM, [2] LARGE, [3] TINY, [4] MID
-   int *count;                // [5]
+   int *list[6];              // [0] SMALL, [1] MEDIUM, [2] LARGE, [3] TINY, [4] MID, [5] MID2
+   int *count;                // [6]
 };
 
 // Precomputed constant tables (host, glibc libm => bit-identical to the oracle), in device memory.
