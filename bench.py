@@ -143,7 +143,7 @@ def _cpu_worker(args):
 
 def ncu_traffic():
     """DRAM bytes (read+write) of one octave-0 k_blur_tma launch from the committed `ncu --set full` capture
-    (profiles/r1c_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
+    (profiles/r1d_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
     path = os.path.join(ROOT, "profiles", "r1b_k_blur_tma_ncu.txt")
     try:
         rd = wr = None
@@ -387,7 +387,7 @@ def main():
                          "algorithmic_bytes_per_image": blur_bytes, "survey_bytes_per_image_incl_nms": survey_bytes,
                          "traffic": ncu_traffic()[0],
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE octave-0 k_blur_tma<11> launch over "
-                                         "32 x 1920x1080 (ncu --set full, profiles/r1c_k_blur_tma_ncu.txt); algorithmic bytes of "
+                                         "32 x 1920x1080 (ncu --set full, profiles/r1d_k_blur_tma_ncu.txt); algorithmic bytes of "
                                          "that launch: %.0f" % (ncu_traffic()[1] or 0)},
             "clocks": clk,
             "host_cores": host_cores, "host_threads": host_threads,
