@@ -195,6 +195,11 @@ def cpu_reference_run(images_u8, over, cores):
 
 
 def main():
+    # Exactly ONE line goes to stdout (the JSON record): library chatter on fd 1 (e.g. NCCL's version banner) is sent to
+    # stderr for the duration of the run.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
