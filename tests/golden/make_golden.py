@@ -2,7 +2,7 @@
 """Generate tests/golden/ from the REFERENCE build (oracle/_ref: perdoch/hesaff sources compiled
 unmodified against oracle/shim). Run in the container that has /root/reference:
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 
 Outputs
   tests/golden/tex_320x240_s11.pgm          input image (textured(320,240,11))
@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle  # noqa: E402
 from tools.gen_textured import textured, write_pgm  # noqa: E402

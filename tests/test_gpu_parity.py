@@ -102,7 +102,7 @@ def test_detections_match_oracle(hb, port_oracle, w, h, seed, over):
 
 
 def test_golden_records_of_reference_build(hb):
-    """Against tests/golden/ (written by the reference's own sources, tools/make_golden.py)."""
+    """Against tests/golden/ (written by the reference's own sources, tests/golden/make_golden.py)."""
     img = read_pgm(os.path.join(GOLDEN, "tex_320x240_s11.pgm"))
     want = np.load(os.path.join(GOLDEN, "tex_320x240_s11.ref.npz"))["dets"]
     det = run(hb, img)

@@ -1,6 +1,6 @@
 """Pins the plain-C oracle (oracle/hesaff_oracle.c) to the reference:
   * bit for bit against oracle/_ref (the reference's own sources, compiled unmodified), per stage and end to end;
-  * against the golden vectors under tests/golden/ that tools/make_golden.py wrote from oracle/_ref.
+  * against the golden vectors under tests/golden/ that tests/golden/make_golden.py wrote from oracle/_ref.
 The reference ships no tests or fixtures of its own, so these are the pins."""
 import hashlib
 import json
