@@ -441,3 +441,35 @@ def test_device_records_and_nccl_keypoint_gather(hb):
     finally:
         dist.destroy_process_group()
     det.close()
+
+
+KNOB_WORKER = r'''
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import hesaff_b200 as hb
+from tools.gen_textured import textured
+imgs = np.stack([textured(480, 360, 90 + s) for s in range(6)])
+det = hb.AffineHessianDetector(hb.HessianAffineParams(), 0, 480, 360, max_batch=2)      # 3 chunks over two lanes
+det.detectPyramidKeypoints(imgs)
+print(hashlib.sha256(det.keys().tobytes()).hexdigest(), det.n_detected.tolist(), det.n_described.tolist())
+'''
+
+
+def test_schedule_knobs_do_not_change_results(hb, tmp_path):
+    """The describe launch plan (which bins run where, with how many CTAs), a plan that leaves bins out, and the
+    front-end / describe overlap across chunk lanes are scheduling only: records are byte-identical."""
+    import subprocess
+    import sys
+    script = tmp_path / "k.py"
+    script.write_text(KNOB_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"HESAFF_OVERLAP": "0"}, {"HESAFF_PLAN": "T2,S2,D1,E1,M1,L1"}, {"HESAFF_PLAN": "S3;L2"},
+                {"HESAFF_PLAN": "L1,M2,E3,D4,S7,T9;T1", "HESAFF_CHUNK": "1"}):
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, str(script), root], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (env, r.stderr[-2000:])
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert len(set(outs)) == 1, outs
