@@ -20,7 +20,9 @@
 
 #define HA_MAX_PATCH_R 519     // largest half-width of a per-patch blur kernel (shared-memory table)
 
+#ifndef HA_BIN_TINY_MAXP
 #define HA_BIN_TINY_MAXP 39    // patch+SIFT kernel bins by source-patch side P
+#endif
 #define HA_BIN_SMALL_MAXP 47
 #define HA_BIN_MID_MAXP 63
 #define HA_BIN_MID2_MAXP 79
