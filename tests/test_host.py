@@ -24,6 +24,37 @@ def test_library_exports_every_declared_symbol():
     assert lib.hesaff_abi_version() == 1
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header compiles as C99 on its own (no C++ or torch types in the signatures)."""
+    r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only",
+                        os.path.join(ROOT, "include", "hesaff_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_tools_do_not_import_the_oracle():
+    """tools/ is product-side tooling (generators, profilers): the oracle stays behind tests/, smoke() and bench.py."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference's CPU code on host cores) on the smallest workload: exactly one stdout
+    line, carrying the keys the contract names."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-images", "2", "--workload", "single_640x480"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("single_640x480")
+
+
 def test_params_default_mirror_reference_structs(port_oracle):
     import hesaff_b200
     p = hesaff_b200.HessianAffineParams()
