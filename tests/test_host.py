@@ -55,6 +55,16 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("single_640x480")
 
 
+def test_bench_roofline_traffic_comes_from_a_committed_ncu_capture():
+    """roofline.traffic is read from the ncu --set full summary under profiles/ that bench.py names."""
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, algorithmic = bench.ncu_traffic()
+    assert traffic and algorithmic and 0.8 < traffic / algorithmic < 1.2, (traffic, algorithmic)
+    blur, survey, n_o = bench.pyramid_algorithmic_bytes(1920, 1080, 3, 5, 0)
+    assert len(n_o) == 7 and blur == 160342800 and survey == 214941000      # SURVEY.md 8(d): 214.9 MB per 1080p image
+
+
 def test_params_default_mirror_reference_structs(port_oracle):
     import hesaff_b200
     p = hesaff_b200.HessianAffineParams()
