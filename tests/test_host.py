@@ -24,6 +24,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.hesaff_abi_version() == 1
 
 
+def test_blur_kernel_sass_uses_tma_and_packed_fp32():
+    """Static proof on the built library (no GPU needed): every k_blur_tma instantiation stages its tile with one TMA
+    box load (UTMALDG.3D) behind an mbarrier (SYNCS.*) and runs its filter passes on packed f32x2 math."""
+    import shutil
+    import hesaff_b200
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", hesaff_b200.lib_path()], capture_output=True, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)
+    blur = [f for f in funcs if f.startswith("_Z10k_blur_tma")]
+    assert len(blur) >= 9, len(blur)                      # 1..21 taps
+    for f in blur:
+        assert f.count("UTMALDG.3D") == 1, f[:80]
+        assert "SYNCS.ARRIVE.TRANS64" in f and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in f, f[:80]
+    wide = [f for f in blur if "ILi11E" in f or "ILi15E" in f]
+    assert wide and all("FFMA2" in f and "FADD2" in f for f in wide)
+    # nothing on the path is a dense contraction: no tensor-core instructions anywhere in the library
+    assert not re.search(r"\b(HMMA|IMMA|UTCHMMA|UTCMMA|QGMMA|HGMMA)\b", sass)
+
+
 def test_header_is_plain_c():
     """The boundary is a C ABI: the header compiles as C99 on its own (no C++ or torch types in the signatures)."""
     r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only",
