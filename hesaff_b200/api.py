@@ -151,17 +151,31 @@ class AffineHessianDetector:
     def detectPyramidKeypoints(self, images, stream=None):
         on_device = 0
         if hasattr(images, "data_ptr"):   # torch tensor
+            import torch
             t = images
+            rgb = t.dim() == 4 and t.shape[3] == 3 and t.dtype == torch.uint8   # [N,H,W,3] interleaved colour
             if t.dim() == 2:
                 t = t.unsqueeze(0)
-            assert t.dim() == 3 and t.stride(2) == 1
+            if not (t.dim() == 3 or rgb) or t.stride(-1) != 1:
+                raise HesaffError("expected a [H,W], [N,H,W] or uint8 [N,H,W,3] tensor with unit innermost stride")
+            if rgb and t.stride(2) != 3:
+                raise HesaffError("interleaved colour input needs a pixel stride of 3 bytes")
+            if t.dtype == torch.uint8:
+                fn = lib().hesaff_detect_rgb8 if rgb else lib().hesaff_detect_u8
+            elif t.dtype == torch.float32:
+                fn = lib().hesaff_detect_f32
+            else:
+                raise HesaffError("unsupported tensor dtype %s (uint8 gray / uint8 RGB / float32 gray)" % t.dtype)
             on_device = 1 if t.is_cuda else 0
-            n, h, w = t.shape
+            n, h, w = t.shape[:3]
             esz = t.element_size()
-            fn = {1: lib().hesaff_detect_u8, 4: lib().hesaff_detect_f32}[esz]
             ptr, rp, ist = t.data_ptr(), t.stride(1) * esz, t.stride(0) * esz
             if n == 1:
                 ist = max(ist, rp * h)
+            if on_device and stream is None:
+                # order the call after the work already queued on the tensor's current torch stream; torch's default
+                # stream is the legacy default stream, whose handle 0 the C-ABI reads as "the context's own stream"
+                stream = torch.cuda.current_stream(t.device).cuda_stream or 1    # 1 = cudaStreamLegacy
             self._keep = t
         else:
             a = np.asarray(images)

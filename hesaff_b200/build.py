@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # HESAFF_LIB selects another build of the same library (tuning experiments: tools/build_variants.py)
 LIB = os.environ.get("HESAFF_LIB") or os.path.join(HERE, "libhesaff_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu", "export.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "hesaff_b200.h")]
+SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu", "describe.cu", "describe_large.cu", "export.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "describe.cuh"), os.path.join(HERE, "..", "include", "hesaff_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

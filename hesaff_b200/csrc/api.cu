@@ -84,6 +84,7 @@ struct hesaff_ctx {
    hesaff_keypoint *host_out; size_t host_out_cap; bool host_out_filled;   // optional streamed host output
    int64_t total_desc, total_det;
    int last_chunks;
+   int last_u8;                // the last call's input was gray u8 (the u8 image copy in the arena is valid)
    bool have_result;
    LaunchCounter lc;
    // profiling (forces single-lane, serialised execution so that stage times are clean)
@@ -247,6 +248,16 @@ static int build_tables(hesaff_ctx *c)
       if (n / 2 > HA_MAX_PATCH_R) return fail(HESAFF_ERR_INVALID, "image too large: the per-patch blur would need more than 1039 taps (sqrt(W*H) must stay below ~4600)");
    }
    c->tables.pk_count = count;
+   {  // fixed-stride copy for the shared-memory bins (P0 <= 93: m <= 46, R <= 10)
+      std::vector<float> pk16(48 * 16, 0.f);
+      for (int m = 0; m < 48 && m < count; m++) {
+         const int R = pn[m] / 2;
+         if (R > 14) break;
+         for (int i = 0; i <= R; i++) pk16[m * 16 + i] = pk[poff[m] + i];
+         pk16[m * 16 + 15] = (float)pn[m];
+      }
+      if ((rc = upload(c, pk16, &c->tables.pk16))) return rc;
+   }
    if ((rc = upload(c, pn, &c->tables.pk_n))) return rc;
    if ((rc = upload(c, poff, &c->tables.pk_off))) return rc;
    if ((rc = upload(c, pk, &c->tables.pk))) return rc;
@@ -274,6 +285,9 @@ static int plan_geometry(const hesaff_params &p, int W, int H, Geom &g)
    g.img_off = off;
    off += align_up((size_t)H * align_up(W, 4), 64);
    if (g.nOct == 0) g.pitch[0] = (int)align_up(W, 4);
+   g.pitch8 = (int)align_up(W, 16);
+   g.img8_off = off;
+   off += align_up(((size_t)H * g.pitch8 + 3) / 4, 64);
    for (o = 0; o < g.nOct; o++)
       for (int l = 0; l < g.S + 2; l++) {
          g.L_off[o][l] = off; off += align_up((size_t)g.h[o] * g.pitch[o], 64);
@@ -434,11 +448,14 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    size_t chunk_cap = 128;   // large chunks amortise the launch-bound small octaves (pyramid stage: 50 -> 40 ms per 1024 x 1080p)
    if (const char *e = getenv("HESAFF_CHUNK")) chunk_cap = (size_t)std::max(1, atoi(e));   // tuning knob (bench experiments)
    if (chunk <= 0) chunk = (int)std::min<size_t>(chunk_cap, std::max<size_t>(1, (size_t)(free_b * 0.45) / (2 * pib)));
+   // work-list entries carry the candidate index in 26 bits (describe.cu): at most 2^26 candidates per chunk
+   if ((size_t)c->max_cand_per_image > (1ull << 26)) return fail(HESAFF_ERR_INVALID, "candidate pool of one image exceeds 2^26");
+   chunk = (int)std::min<size_t>((size_t)chunk, (1ull << 26) / (size_t)c->max_cand_per_image);
    c->n_lanes = 2;
    if ((size_t)chunk * pib * 2 > free_b * 0.85) c->n_lanes = 1;
    if ((size_t)chunk * pib * c->n_lanes > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");
    c->chunk = chunk;
-   if ((size_t)chunk * c->max_cand_per_image >= 0xFFFFFFF0ull) return fail(HESAFF_ERR_INVALID, "candidate pool exceeds 32-bit indexing");
+
    c->cand_cap = (uint32_t)((size_t)chunk * c->max_cand_per_image);
 
    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -453,7 +470,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    c->mask_words_cap = g.mask_stride * chunk;
    c->scan_tmp_elems = std::max(ha_scan_tmp_elems(c->mask_words_cap), ha_scan_tmp_elems(c->cand_cap)) + 8;
    c->map_elems_cap = g.map_stride * chunk;
-   c->large_ctas = 148 * 2;
+   c->large_ctas = 148 * 3;
    c->scratch_per_cta = align_up(ha_describe_scratch_floats(c->maxP), 64);
    for (int l = 0; l < c->n_lanes; l++)
       if ((rc = alloc_lane(c, c->lane[l], g))) return rc;
@@ -522,6 +539,12 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       return fail(HESAFF_ERR_INVALID, "row pitch / image stride too small");
    CK(cudaSetDevice(c->device));
    cudaStream_t ust = stream_ ? (cudaStream_t)stream_ : c->stream;
+   if (on_device && !stream_) {
+      // stream == NULL means the context's own (non-blocking) stream, NOT the default stream: order it after whatever
+      // the caller queued on the legacy default stream (the usual producer of a device-resident input)
+      CK(cudaEventRecord(c->ev_start, cudaStreamLegacy));
+      CK(cudaStreamWaitEvent(ust, c->ev_start, 0));
+   }
    c->have_result = false;
    c->host_out_filled = false;
 
@@ -557,6 +580,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
    c->blur_ms = 0.f; c->blur_launches = 0;
    c->n_images = n;
    c->last_chunks = 0;
+   c->last_u8 = fmt == IN_U8;
    const int S = g.S;
    const int lanes = c->profiling ? 1 : c->n_lanes;
    for (int l = 0; l < c->n_lanes; l++) {
@@ -598,7 +622,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       if (overlap) { if (prev_front) CK(cudaStreamWaitEvent(st, prev_front, 0)); }
       else if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
       float *img_plane = L.arena + g.img_off;
-      if (fmt == IN_U8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
+      if (fmt == IN_U8) ha_launch_convert_u8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, L.arena, g, cn, st, c->lc);
       else if (fmt == IN_RGB8) ha_launch_convert_rgb8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[1], st);
@@ -665,7 +689,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
 
       // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
       ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
-                         c->large_ctas, c->maxP, nullptr, 0, nullptr, st, c->lc, L.aux, L.ev_fork, L.ev_join);
+                         c->large_ctas, c->maxP, fmt == IN_U8, nullptr, 0, nullptr, st, c->lc, L.aux, L.ev_fork, L.ev_join);
       if (c->profiling) cudaEventRecord(L.ev[5], st);
 
       // ---- stage 5: ordered compaction into Keypoint records -------------------------------------------
@@ -853,7 +877,7 @@ extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, s
    Lane &L = c->lane[0];
    CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 6, L.stream));
    ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
-                      c->large_ctas, c->maxP, d, normalized, L.desc_off, L.stream, c->lc);
+                      c->large_ctas, c->maxP, c->last_u8, d, normalized, L.desc_off, L.stream, c->lc);
    CK(cudaStreamSynchronize(L.stream));
    cudaError_t e = cudaMemcpy(out, d, sizeof(float) * HA_PATCH_PX * c->total_desc, cudaMemcpyDeviceToHost);
    cudaFree(d);

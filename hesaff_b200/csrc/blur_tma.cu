@@ -319,15 +319,18 @@ static int launch_tma_n(const float *src, const Blur3Args &a, const Taps &taps, 
    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -1;
-   static bool attr_set = false;   // one static per instantiation
-   if (!attr_set) {
+   // the attribute is per device (a process may hold contexts on several GPUs): cache it per device index
+   static bool attr_set[64] = {};   // one array per instantiation
+   int dev = 0;
+   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       if (cudaFuncSetAttribute(k_blur_tma<N, OH, NT, MINB, SHIFT, SHFL_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
          return -1;
-      attr_set = true;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
    }
    dim3 grid((a.W + TW - 1) / TW, (a.H + C::TH - 1) / C::TH, n);
    k_blur_tma<N, OH, NT, MINB, SHIFT, SHFL_EDGES><<<grid, NT, C::SMEM, st>>>(tm, a, taps);
-   return 0;
+   return cudaGetLastError() == cudaSuccess ? 0 : -1;   // a failed launch falls back to k_blur (pyramid.cu)
 }
 
 #ifndef HA_BLUR_VARIANTS

@@ -42,6 +42,8 @@ struct Geom {
    int border;               // PyramidParams.border
    int w[HA_MAX_OCT], h[HA_MAX_OCT], pitch[HA_MAX_OCT];   // pitch in floats, multiple of 4
    unsigned long long img_off;                             // float image (original), pitch[0]
+   unsigned long long img8_off;                            // u8 copy of a gray 8-bit input (floats from the arena base), row pitch pitch8
+   int pitch8;                                             // bytes, multiple of 16
    unsigned long long L_off[HA_MAX_OCT][HA_MAX_LVL];       // blur planes, floats from the image's arena base
    unsigned long long R_off[HA_MAX_OCT][HA_MAX_LVL];       // response planes
    unsigned long long arena_stride;                        // floats between consecutive images
@@ -113,6 +115,7 @@ struct Tables {
    const int *pk_off;
    const float *pk;
    int pk_count;
+   const float *pk16;         // [48][16] the same half kernels for m <= 47 (R <= 10) at a fixed stride, [m][15] = n
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -139,7 +142,7 @@ struct LaunchCounter {
    long long n;
 };
 
-void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
+void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *arena, const Geom &g, int n,
                           cudaStream_t st, LaunchCounter &lc);
 void ha_launch_convert_rgb8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
                             cudaStream_t st, LaunchCounter &lc);
@@ -174,7 +177,7 @@ void ha_launch_localize(const float *arena, const Geom *dg, Cand cand, const uin
 void ha_launch_affine(const float *arena, const Geom *dg, Tables tb, Cand cand, const uint32_t *count, uint32_t cap,
                       const uint32_t *map, int *n_det, Bins bins, int *work_counter, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_describe(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,
-                        float *scratch, size_t scratch_per_cta, int large_ctas, int maxP, float *patch_dump,
+                        float *scratch, size_t scratch_per_cta, int large_ctas, int maxP, int src_u8, float *patch_dump,
                         int dump_normalized, const uint32_t *dump_index, cudaStream_t st, LaunchCounter &lc,
                         cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 void ha_launch_compact(Cand cand, const uint32_t *count, uint32_t cap, const uint32_t *desc_off, const Geom *dg,
@@ -182,5 +185,5 @@ void ha_launch_compact(Cand cand, const uint32_t *count, uint32_t cap, const uin
                        int *overflow, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_export_detections(Cand cand, const uint32_t *count, uint32_t cap, const uint32_t *det_off,
                                  const Geom *dg, hesaff_detection *out, cudaStream_t st, LaunchCounter &lc);
-int ha_describe_smem_bytes(int bin, int maxP);
+int ha_describe_smem_bytes(int bin);
 size_t ha_describe_scratch_floats(int maxP);

@@ -16,21 +16,26 @@
 // =================================================================================================
 // input conversion (hesaff.cpp:138-148: gray = (B+G+R)/3.0f, exact for gray input)
 // =================================================================================================
-__global__ void k_convert_u8(const uint8_t *__restrict__ src, size_t row_pitch, size_t img_stride, float *__restrict__ dst,
-                             int W, int H, int pitch, unsigned long long arena_stride)
+__global__ void k_convert_u8(const uint8_t *__restrict__ src, size_t row_pitch, size_t img_stride, float *__restrict__ arena,
+                             int W, int H, int pitch, int pitch8, unsigned long long img_off, unsigned long long img8_off,
+                             unsigned long long arena_stride)
 {
+   // 4 pixels per thread: the float gray image (hesaff.cpp:138-148: B = G = R for a gray file, (3v)/3.0f = v) and a
+   // 16-byte-pitched u8 copy, the exact source of the affine patch sampling (describe.cu)
    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
    const int y = blockIdx.y;
    const int n = blockIdx.z;
-   if (x >= W) return;
+   if (x >= pitch8) return;
    const uint8_t *s = src + (size_t)n * img_stride + (size_t)y * row_pitch + x;
-   float *d = dst + (size_t)n * arena_stride + (size_t)y * pitch + x;
-   float4 v;
-   v.x = (float)s[0];
-   v.y = x + 1 < W ? (float)s[1] : 0.f;
-   v.z = x + 2 < W ? (float)s[2] : 0.f;
-   v.w = x + 3 < W ? (float)s[3] : 0.f;
-   *reinterpret_cast<float4 *>(d) = v;   // pitch is a multiple of 4 floats
+   uchar4 b = make_uchar4(0, 0, 0, 0);
+   if (x < W) b.x = s[0];
+   if (x + 1 < W) b.y = s[1];
+   if (x + 2 < W) b.z = s[2];
+   if (x + 3 < W) b.w = s[3];
+   float *base = arena + (size_t)n * arena_stride;
+   *reinterpret_cast<uchar4 *>(reinterpret_cast<unsigned char *>(base + img8_off) + (size_t)y * pitch8 + x) = b;
+   if (x < pitch)
+      *reinterpret_cast<float4 *>(base + img_off + (size_t)y * pitch + x) = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);   // pitch is a multiple of 4 floats
 }
 
 __global__ void k_convert_f32(const float *__restrict__ src, size_t row_pitch_bytes, size_t img_stride_bytes,
@@ -65,11 +70,12 @@ void ha_launch_convert_rgb8(const uint8_t *src, size_t row_pitch, size_t img_str
    lc.n++;
 }
 
-void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *dst, const Geom &g, int n,
+void ha_launch_convert_u8(const uint8_t *src, size_t row_pitch, size_t img_stride, float *arena, const Geom &g, int n,
                           cudaStream_t st, LaunchCounter &lc)
 {
-   dim3 grid((g.W + 4 * 128 - 1) / (4 * 128), g.H, n);
-   k_convert_u8<<<grid, 128, 0, st>>>(src, row_pitch, img_stride, dst, g.W, g.H, g.pitch[0], g.arena_stride);
+   dim3 grid((g.pitch8 + 4 * 128 - 1) / (4 * 128), g.H, n);
+   k_convert_u8<<<grid, 128, 0, st>>>(src, row_pitch, img_stride, arena, g.W, g.H, g.pitch[0], g.pitch8, g.img_off, g.img8_off,
+                                      g.arena_stride);
    lc.n++;
 }
 

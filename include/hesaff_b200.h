@@ -103,8 +103,11 @@ int hesaff_destroy(hesaff_ctx *ctx);
  *   hesaff_detect_rgb8 : 8-bit, 3 interleaved channels (what imread hands to main(), hesaff.cpp:137); the gray
  *                        conversion (float(c0)+c1+c2)/3.0f of hesaff.cpp:145 runs on the GPU
  * `on_device` != 0 means `images` is a device pointer on the context's GPU; otherwise it is host memory
- * (pinned memory makes the upload asynchronous).  `stream` is a cudaStream_t (NULL = the context's own
- * stream); the call returns after the work is enqueued AND the per-image counts are known on the host.
+ * (pinned memory makes the upload asynchronous).  `stream` is a cudaStream_t; NULL selects the context's own
+ * non-blocking stream -- it does NOT mean the CUDA default stream (pass cudaStreamLegacy / cudaStreamPerThread for
+ * those).  With NULL and a device-resident input the call is ordered after the work already queued on the legacy
+ * default stream; input produced on any other stream must be passed together with that stream.  The call returns
+ * after the work is enqueued AND the per-image counts are known on the host.
  * Results stay on the device until the next hesaff_detect_* call on this context. */
 int hesaff_detect_u8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
                      size_t image_stride_bytes, int on_device, void *stream);
