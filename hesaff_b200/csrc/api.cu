@@ -218,7 +218,9 @@ static int build_tables(hesaff_ctx *c)
             } else outside.push_back((uint32_t)t);
          }
       for (int t = 0; t < HA_PATCH_PX; t++) {
-         const uint32_t w = (uint32_t)t | ((uint32_t)(t / HA_PATCH) << 16) | ((uint32_t)(t % HA_PATCH) << 24);
+         // patch index | needed << 14 | inside the disc << 15 | row << 16 | column << 24
+         const uint32_t w = (uint32_t)t | (needed[t] ? 0x4000u : 0u) | (m41[t] > 0 ? 0x8000u : 0u) |
+                            ((uint32_t)(t / HA_PATCH) << 16) | ((uint32_t)(t % HA_PATCH) << 24);
          all.push_back(w);
          if (needed[t]) need.push_back(w);
       }

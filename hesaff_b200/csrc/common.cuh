@@ -107,7 +107,7 @@ struct Tables {
    // The mask is zero outside a disc that never touches the patch border, so the SIFT passes run over lists:
    const uint2 *sift_disc;    // [HA_SIFT_ND] {patch index r*41+c, mask weight bits} of the pixels inside the disc, raster order
    const uint32_t *sift_out;  // [41*41 - HA_SIFT_ND] patch indices outside the disc
-   const uint32_t *sift_need; // [HA_SIFT_NN] index | row << 16 | col << 24 of the disc pixels and their 4-neighbours
+   const uint32_t *sift_need; // [HA_SIFT_NN] index | needed << 14 | in-disc << 15 | row << 16 | col << 24 of the disc pixels and their 4-neighbours
    const uint32_t *sift_all;  // [41*41] the same packing for every pixel (patch dumps)
    // per-patch blur kernels indexed by m = (P0-1)/2 (P0 = 2*int(mrScale)+1): taps n and offset of the
    // R+1 half kernel k[R..n-1] in `pk`

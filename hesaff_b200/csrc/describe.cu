@@ -230,9 +230,6 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
    const int cols = g->W, rows = g->H, pitch = g->pitch[0], pitch8 = g->pitch8;
    const float mrSize = g->mrSize;
    const unsigned long long arena_stride = g->arena_stride, img_off = g->img_off, img8_off = g->img8_off;
-   // patch pixels the descriptor can depend on (everything when the patches are dumped for the tests)
-   const uint32_t *__restrict__ rs_list = patch_dump ? tb.sift_all : tb.sift_need;
-   const int rs_n = patch_dump ? HA_PATCH_PX : HA_SIFT_NN;
 
    // prefetch pipeline state (thread 0): ticket of item k+2, list entry of item k+1 (HA_LIST_NONE: none)
    int pf_w = -1;
@@ -412,42 +409,40 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
 #undef HA_PB
                default: ha_patch_blur_generic<NT>(S, T, P, n, kern);
             }
-            for (int e = tid; e < rs_n; e += NT) {
-               const uint32_t w = __ldg(rs_list + e);
-               const int jj = (w >> 16) & 0xff, ii = w >> 24;
-               const float *p = S + rs_r[jj] + rs_i[ii];
-               patch[w & 0xffff] = ha_bilinear(p[0], p[1], p[P], p[P + 1], rs_f[ii], rs_f[jj]);
-            }
 #endif
-         } else if (!rejected) {
-            // lots of oversampling: sample the 41x41 patch directly (affine.cpp:135-142)
-            const float *__restrict__ im = arena + (size_t)it.img * arena_stride + img_off;
-            const float b11 = a11 * its, b12 = a12 * its, b21 = a21 * its, b22 = a22 * its;
-            for (int t = tid; t < HA_PATCH_PX; t += NT) {
-               const int jj = t / HA_PATCH, j = jj - (HA_PATCH >> 1), ii = t - jj * HA_PATCH - (HA_PATCH >> 1);
-               const float rx = x + j * b12, ry = y + j * b22;
-               float wx = rx + ii * b11, wy = ry + ii * b21;
-               const int xi = (int)floorf(wx), yi = (int)floorf(wy);
-               float v = 0.f;
-               if (xi >= 0 && yi >= 0 && xi < cols - 1 && yi < rows - 1) {
-                  wx -= xi; wy -= yi;
-                  const float *p = im + (size_t)yi * pitch + xi;
-                  v = ha_bilinear(p[0], p[1], p[pitch], p[pitch + 1], wx, wy);
-               }
-               patch[t] = v;
-            }
          }
          if (!rejected) {   // uniform across the CTA
 #if defined(HA_ABL) && HA_ABL == 1
             if (tid == 0) cand.flags[i] |= HA_F_DESC;
 #else
-            __syncthreads();
-            if (patch_dump && !dump_normalized) {
-               float *d = patch_dump + (size_t)dump_index[i] * HA_PATCH_PX;
-               for (int t = tid; t < HA_PATCH_PX; t += NT) d[t] = patch[t];
+            float *dump = patch_dump ? patch_dump + (size_t)dump_index[i] * HA_PATCH_PX : nullptr;
+            float *dump_raw = dump_normalized ? nullptr : dump, *dump_norm = dump_normalized ? dump : nullptr;
+            unsigned char *desc = cand.desc + (size_t)i * 128;
+            if (!oversampled) {
+               // interpolate(smoothed, P>>1, P>>1, its, 0, 0, its, patch) (affine.cpp:131): axis aligned, tables above
+               const float *S = regA;
+               ha_sift_describe<NT>([&](int jj, int ii) {
+                  const float *p = S + rs_r[jj] + rs_i[ii];
+                  return ha_bilinear(p[0], p[1], p[P], p[P + 1], rs_f[ii], rs_f[jj]);
+               }, sh.red, patch, v01, voff, acc, tb, desc, dump_raw, dump_norm);
+            } else {
+               // lots of oversampling: sample the 41x41 patch directly (affine.cpp:135-142); zeros outside the image
+               const float *__restrict__ im = arena + (size_t)it.img * arena_stride + img_off;
+               const float b11 = a11 * its, b12 = a12 * its, b21 = a21 * its, b22 = a22 * its;
+               ha_sift_describe<NT>([&](int jj, int ii) {
+                  const int j = jj - (HA_PATCH >> 1), ic = ii - (HA_PATCH >> 1);
+                  const float rx = x + j * b12, ry = y + j * b22;
+                  float wx = rx + ic * b11, wy = ry + ic * b21;
+                  const int xi = (int)floorf(wx), yi = (int)floorf(wy);
+                  float v = 0.f;
+                  if (xi >= 0 && yi >= 0 && xi < cols - 1 && yi < rows - 1) {
+                     wx -= xi; wy -= yi;
+                     const float *p = im + (size_t)yi * pitch + xi;
+                     v = ha_bilinear(p[0], p[1], p[pitch], p[pitch + 1], wx, wy);
+                  }
+                  return v;
+               }, sh.red, patch, v01, voff, acc, tb, desc, dump_raw, dump_norm);
             }
-            ha_sift_describe<NT>(sh.red, patch, v01, voff, acc, tb, cand.desc + (size_t)i * 128,
-                                 (patch_dump && dump_normalized) ? patch_dump + (size_t)dump_index[i] * HA_PATCH_PX : nullptr);
             if (tid == 0) cand.flags[i] |= HA_F_DESC;
 #endif
          }

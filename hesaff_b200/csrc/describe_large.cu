@@ -67,8 +67,6 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
    float2 *acc = reinterpret_cast<float2 *>(rowbuf);
    const int tid = threadIdx.x;
    const int nwork = *list_n;
-   const uint32_t *__restrict__ rs_list = patch_dump ? tb.sift_all : tb.sift_need;
-   const int rs_n = patch_dump ? HA_PATCH_PX : HA_SIFT_NN;
    const int cols = g->W, rows = g->H;
    const int spitch = U8 ? g->pitch8 : g->pitch[0];
    float *__restrict__ T = scratch + (size_t)blockIdx.x * scratch_per_cta;
@@ -227,19 +225,14 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
          *reinterpret_cast<ha_f2 *>(B + (2 * jy + 1) * 82 + 2 * q2) = acc1;
       }
       __syncthreads();
-      for (int e = tid; e < rs_n; e += NT) {
-         const uint32_t w = __ldg(rs_list + e);
-         const int jj = (w >> 16) & 0xff, ii = w >> 24;
-         const float *p = B + (2 * jj) * 82 + 2 * ii;
-         patch[w & 0xffff] = ha_bilinear(p[0], p[1], p[82], p[83], sh.rs_f[ii], sh.rs_f[jj]);
+      {
+         float *dump = patch_dump ? patch_dump + (size_t)dump_index[i] * HA_PATCH_PX : nullptr;
+         // interpolate(smoothed, P>>1, P>>1, its, 0, 0, its, patch) (affine.cpp:131) from the 82 x 82 blurred grid
+         ha_sift_describe<NT>([&](int jj, int ii) {
+            const float *p = B + (2 * jj) * 82 + 2 * ii;
+            return ha_bilinear(p[0], p[1], p[82], p[83], sh.rs_f[ii], sh.rs_f[jj]);
+         }, sh.red, patch, v01, voff, acc, tb, cand.desc + (size_t)i * 128, dump_normalized ? nullptr : dump, dump_normalized ? dump : nullptr);
       }
-      __syncthreads();
-      if (patch_dump && !dump_normalized) {
-         float *d = patch_dump + (size_t)dump_index[i] * HA_PATCH_PX;
-         for (int t = tid; t < HA_PATCH_PX; t += NT) d[t] = patch[t];
-      }
-      ha_sift_describe<NT>(sh.red, patch, v01, voff, acc, tb, cand.desc + (size_t)i * 128,
-                           (patch_dump && dump_normalized) ? patch_dump + (size_t)dump_index[i] * HA_PATCH_PX : nullptr);
       if (tid == 0) cand.flags[i] |= HA_F_DESC;
    }
 }

@@ -9,6 +9,10 @@ Outputs
   tests/golden/tex_320x240_s11.ref.npz      every per-detection record of the reference (oracle.DET_DTYPE)
   tests/golden/tex_320x240_s11.hesaff.sift  the reference CLI's output file for that image
   tests/golden/summary.json                 counts + sha256 of the record bytes for larger images / other params
+  tests/golden/full_<name>.npz              BASELINE-size frames (1080p default; 4K S=10 3 octaves; 4096^2 thr 5 6 octaves):
+                                            every STRIDE-th per-detection record of the reference, whole-frame counts and
+                                            the sha256 of the bit-exact detection fields (x, y, pd, type, response) of ALL
+                                            detections -- what tests/test_gpu_parity.py::test_full_frames_* compare with
 """
 import hashlib
 import json
@@ -34,6 +38,36 @@ CASES = [  # name, w, h, seed, param overrides
 ]
 
 
+FULL = [  # name, w, h, seed, overrides, record stride      (SURVEY.md 8(c) fixtures / BASELINE.json configs 2, 1, 4)
+    ("full_1080p_s2", 1920, 1080, 2, {}, 16),
+    ("full_4k_s3_S10_oct3", 3840, 2160, 3, {"number_of_scales": 10, "max_octaves": 3}, 64),
+    ("full_4096_s5_thr5_oct6", 4096, 4096, 5, {"threshold": 5.0, "max_octaves": 6}, 64),
+]
+
+
+def detection_hash(d):
+    """sha256 over the fields the CUDA path reproduces bit for bit, in reference order"""
+    h = hashlib.sha256()
+    for f in ("x", "y", "pd", "type", "response"):
+        h.update(np.ascontiguousarray(d[f]).tobytes())
+    return h.hexdigest()
+
+
+def full_frames(ref, summary):
+    for name, w, h, seed, over, stride in FULL:
+        img = textured(w, h, seed)
+        d = ref.detect(img.astype(np.float32), ref.default_params(**over))
+        summary[name] = {
+            "w": w, "h": h, "seed": seed, "params": over, "stride": stride,
+            "image_sha256": hashlib.sha256(img.tobytes()).hexdigest(),
+            "detections": int(len(d)), "affine": int(d["affine_ok"].sum()), "described": int(d["described"].sum()),
+            "detection_fields_sha256": detection_hash(d),
+            "records_sha256": hashlib.sha256(d.tobytes()).hexdigest(),
+        }
+        print(name, summary[name]["detections"], summary[name]["described"], flush=True)
+        np.savez_compressed(os.path.join(G, name + ".npz"), index=np.arange(0, len(d), stride), dets=d[::stride])
+
+
 def main():
     oracle.build(ref=True)
     ref = oracle.load("ref")
@@ -55,6 +89,8 @@ def main():
             np.savez_compressed(os.path.join(G, name + ".ref.npz"), dets=d)
             subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "hesaff_ref"), pgm])
             os.replace(pgm + ".hesaff.sift", os.path.join(G, name + ".hesaff.sift"))
+    if "--no-full" not in sys.argv:
+        full_frames(ref, summary)
     with open(os.path.join(G, "summary.json"), "w") as f:
         json.dump(summary, f, indent=1, sort_keys=True)
 

@@ -473,3 +473,68 @@ def test_schedule_knobs_do_not_change_results(hb, tmp_path):
         assert r.returncode == 0, (env, r.stderr[-2000:])
         outs.append(r.stdout.strip().splitlines()[-1])
     assert len(set(outs)) == 1, outs
+
+
+# ---- whole frames at the BASELINE sizes ---------------------------------------------------------------------
+FULL_FRAMES = [
+    ("full_1080p_s2", 1920, 1080, 2, {}),                                                   # BASELINE configs[2] frame
+    ("full_4k_s3_S10_oct3", 3840, 2160, 3, {"number_of_scales": 10, "max_octaves": 3}),    # BASELINE configs[1]
+    ("full_4096_s5_thr5_oct6", 4096, 4096, 5, {"threshold": 5.0, "max_octaves": 6}),        # BASELINE configs[4]
+]
+
+
+def _detection_hash(d):
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("x", "y", "pd", "type", "response"):
+        h.update(np.ascontiguousarray(d[f]).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name,w,h,seed,over", FULL_FRAMES)
+def test_full_frames_match_golden_of_the_reference_build(hb, name, w, h, seed, over):
+    """The WHOLE frame against tests/golden/full_*.npz, written by the reference's own sources (make_golden.py): detection
+    count, sha256 of every detection's bit-exact fields, and every STRIDE-th full record within north_star's tolerances."""
+    summ = json.load(open(os.path.join(GOLDEN, "summary.json")))[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    img = textured(w, h, seed)
+    import hashlib
+    assert hashlib.sha256(img.tobytes()).hexdigest() == summ["image_sha256"]
+    det = run(hb, img, **over)
+    got = det.detections()
+    assert len(got) == summ["detections"] == int(det.n_detected[0])
+    assert _detection_hash(got) == summ["detection_fields_sha256"]
+    slack = max(2, int(0.0005 * summ["detections"]))
+    assert abs(int(got["affine_ok"].sum()) - summ["affine"]) <= slack
+    assert abs(int(det.n_described[0]) - summ["described"]) <= slack
+    idx, want = gold["index"], gold["dets"]
+    sub = got[idx]
+    for f in ("x", "y", "pd", "type", "response"):
+        assert np.array_equal(sub[f], want[f]), f
+    same = (sub["affine_ok"] == want["affine_ok"]) & (sub["described"] == want["described"])
+    assert (~same).sum() <= max(1, int(0.002 * len(want)))
+    both = same & (want["described"] == 1)
+    st = compare_keypoints(sub[both], want[both], mr_size=det.par.desc_factor)
+    assert st["aligned"] == int(both.sum()) and st["within_tol_frac"] >= 0.998, st
+    assert st["desc_within_1_frac"] >= 0.995, st
+    det.close()
+
+
+def test_full_1080p_frame_against_the_reference_build_directly(hb, ref_oracle):
+    """One hop instead of two: the CUDA path against oracle/_ref (the reference's own translation units, which travel to
+    the GPU box as a built library) on a whole 1920x1080 frame, every record."""
+    img = textured(1920, 1080, 2)
+    want = ref_oracle.detect(img.astype(np.float32))
+    det = run(hb, img)
+    got = det.detections()
+    assert len(got) == len(want) > 38000
+    for f in ("x", "y", "pd", "type", "response"):
+        assert np.array_equal(got[f], want[f]), f
+    slack = int(0.0005 * len(want))
+    assert (got["affine_ok"] != want["affine_ok"]).sum() <= slack
+    assert (got["described"] != want["described"]).sum() <= slack
+    kw = want[want["described"] == 1]
+    assert len(kw) > 36000
+    st = compare_keypoints(det.keys(), kw, mr_size=det.par.desc_factor)
+    assert st["aligned"] >= len(kw) - slack and st["within_tol_frac"] * len(kw) >= len(kw) - 2 * slack, st
+    det.close()
