@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <fstream>
 #include <sstream>
 #include "common.cuh"
@@ -184,6 +185,55 @@ static void sift_mask(float *mask, int size)
       }
 }
 
+// Reorders a pixel list so that every aligned group of 32 entries (= the pixels one warp touches in one round) holds 32
+// different patch indices mod 32, lane l and lane l + 16 in bank pairs 16 apart: the scattered shared-memory accesses of
+// the SIFT passes (patch[idx +- 1], patch[idx +- 41], float2 v01[idx]) are then free of bank conflicts.  The passes are
+// order independent per pixel.
+template <typename T, typename F> static void bank_order(std::vector<T> &v, F index_of)
+{
+   std::vector<std::vector<T>> bucket(32);
+   for (const T &e : v) bucket[index_of(e) & 31].push_back(e);
+   for (auto &b : bucket) std::reverse(b.begin(), b.end());   // pop_back takes them in raster order
+   std::vector<T> out;
+   out.reserve(v.size());
+   size_t left = v.size();
+   while (left) {
+      // the last group may have to take two of a residue; until then, one per residue, fullest buckets first
+      std::vector<int> order(32);
+      for (int i = 0; i < 32; i++) order[i] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+      std::vector<int> lane_res(32, -1);
+      size_t take = std::min<size_t>(32, left);
+      std::vector<int> chosen;
+      for (int i = 0; i < 32 && chosen.size() < take; i++)
+         if (!bucket[order[i]].empty()) chosen.push_back(order[i]);
+      std::sort(chosen.begin(), chosen.end());
+      // residue r goes to lane r when free (lanes 0..15 <-> residues 0..15, lanes 16..31 <-> 16..31)
+      std::vector<T> group;
+      std::vector<char> used(32, 0);
+      std::vector<int> lane_of(chosen.size(), -1);
+      for (size_t k = 0; k < chosen.size(); k++)
+         if ((size_t)chosen[k] < take && !used[chosen[k]]) { lane_of[k] = chosen[k]; used[chosen[k]] = 1; }
+      for (size_t k = 0; k < chosen.size(); k++)
+         if (lane_of[k] < 0)
+            for (size_t l = 0; l < take; l++)
+               if (!used[l]) { lane_of[k] = (int)l; used[l] = 1; break; }
+      group.resize(take);
+      for (size_t k = 0; k < chosen.size(); k++) { group[lane_of[k]] = bucket[chosen[k]].back(); bucket[chosen[k]].pop_back(); }
+      // fewer non-empty buckets than slots: fill the free lanes from the fullest buckets
+      for (size_t l = 0; l < take; l++)
+         if (!used[l]) {
+            int best = 0;
+            for (int i = 1; i < 32; i++) if (bucket[i].size() > bucket[best].size()) best = i;
+            group[l] = bucket[best].back();
+            bucket[best].pop_back();
+         }
+      for (const T &e : group) out.push_back(e);
+      left -= group.size();
+   }
+   v.swap(out);
+}
+
 template <typename T> static int upload(hesaff_ctx *c, const std::vector<T> &h, const T **d)
 {
    void *p = nullptr;
@@ -225,6 +275,9 @@ static int build_tables(hesaff_ctx *c)
          if (needed[t]) need.push_back(w);
       }
       if (disc.size() != HA_SIFT_ND || need.size() != HA_SIFT_NN) return fail(HESAFF_ERR_INVALID, "SIFT mask geometry differs from HA_SIFT_ND / HA_SIFT_NN");
+      bank_order(disc, [](const uint2 &e) { return e.x; });
+      bank_order(outside, [](uint32_t e) { return e; });
+      // (the need / all lists stay in raster order: their pass reads neighbouring taps of the blurred patch)
       if ((rc = upload(c, disc, &c->tables.sift_disc))) return rc;
       if ((rc = upload(c, outside, &c->tables.sift_out))) return rc;
       if ((rc = upload(c, need, &c->tables.sift_need))) return rc;

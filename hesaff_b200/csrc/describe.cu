@@ -178,8 +178,7 @@ template <int BIN> struct DescPlan {
    static constexpr int SB1 = SB0 > ACC ? SB0 : ACC;
    static constexpr int SB = ((SB1 > HA_PATCH_PX + 3 ? SB1 : HA_PATCH_PX + 3) + 3) & ~3;   // region B: box, T, patch, then acc
    static constexpr int TABF = 4 * ((MAXP + 3) & ~3) + ((MAXP + 3) & ~3) + 3 * 44;   // ctab (float4), rtab, rs_f, rs_i, rs_r
-   static constexpr int VOFF = (HA_PATCH_PX + 3) / 4 + 1;                 // bytes / 4
-   static constexpr int SC = TABF > VOFF ? TABF : VOFF;                   // region C: sampling tables, then voff
+   static constexpr int SC = (TABF + 3) & ~3;                             // region C: sampling tables
    static constexpr int KN = 16;                                          // taps k[R..n-1] (R <= 10), [15] = n
 };
 
@@ -198,7 +197,10 @@ template <int NT> struct DescHead {
 #define HA_LIST_NONE 0xffffffffu
 
 // resident CTAs per SM the register budget is set for (shared memory allows as many)
-#define DESC_MINB(BIN) ((BIN) == 3 ? 9 : ((BIN) == 0 ? 7 : ((BIN) == 4 ? 4 : ((BIN) == 5 ? 3 : 2))))
+#ifndef DESC_MINB_TINY
+#define DESC_MINB_TINY 8
+#endif
+#define DESC_MINB(BIN) ((BIN) == 3 ? DESC_MINB_TINY : ((BIN) == 0 ? 7 : ((BIN) == 4 ? 4 : ((BIN) == 5 ? 3 : 2))))
 
 template <int BIN, int NT, bool U8>
 __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__restrict__ arena, const Geom *__restrict__ g, Tables tb,
@@ -221,7 +223,6 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
    int *rs_r = rs_i + 44;                                    //                   integer part times the row stride
    // SIFT
    float2 *v01 = reinterpret_cast<float2 *>(regA);
-   unsigned char *voff = reinterpret_cast<unsigned char *>(regC);
    float2 *acc = reinterpret_cast<float2 *>(regB);
    float *patch = regB;
 
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
                ha_sift_describe<NT>([&](int jj, int ii) {
                   const float *p = S + rs_r[jj] + rs_i[ii];
                   return ha_bilinear(p[0], p[1], p[P], p[P + 1], rs_f[ii], rs_f[jj]);
-               }, sh.red, patch, v01, voff, acc, tb, desc, dump_raw, dump_norm);
+               }, sh.red, patch, v01, acc, tb, desc, dump_raw, dump_norm);
             } else {
                // lots of oversampling: sample the 41x41 patch directly (affine.cpp:135-142); zeros outside the image
                const float *__restrict__ im = arena + (size_t)it.img * arena_stride + img_off;
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
                      v = ha_bilinear(p[0], p[1], p[pitch], p[pitch + 1], wx, wy);
                   }
                   return v;
-               }, sh.red, patch, v01, voff, acc, tb, desc, dump_raw, dump_norm);
+               }, sh.red, patch, v01, acc, tb, desc, dump_raw, dump_norm);
             }
             if (tid == 0) cand.flags[i] |= HA_F_DESC;
 #endif
@@ -467,7 +468,7 @@ template <int BIN, int NT> static constexpr int desc_smem()
 
 int ha_describe_smem_bytes(int bin)
 {
-   static_assert(9 * (desc_smem<3, 128>() + 1024) <= 227 * 1024, "TINY: 9 CTAs per SM");
+   static_assert(DESC_MINB_TINY * (desc_smem<3, 128>() + 1024) <= 227 * 1024, "TINY: shared memory of DESC_MINB_TINY CTAs per SM");
    switch (bin) {
       case 3: return desc_smem<3, 128>();
       case 0: return desc_smem<0, 128>();
@@ -504,7 +505,7 @@ static void launch_desc(const DescLaunch &a, int ctas_per_sm, cudaStream_t st)
 static const char *describe_plan()
 {
    static const char *e = getenv("HESAFF_PLAN");
-   return e ? e : "T6,S5,D3,E2,M1;L3,M1";
+   return e ? e : "T8,S5,D3,E2,M1;L3,M1";
 }
 
 void ha_launch_describe(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,

@@ -23,6 +23,7 @@
 
 #define LG_NT 256
 #define LG_B (82 * 82)
+#define LG_TS 84             // row stride of the row-filtered scratch plane T (floats; rows 16-byte aligned)
 
 struct LargeHead {
    float red[2 * (LG_NT / 32)];
@@ -58,8 +59,7 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
    extern __shared__ __align__(16) unsigned char dsm[];
    LargeHead &sh = *reinterpret_cast<LargeHead *>(dsm);
    float2 *kh2 = reinterpret_cast<float2 *>(dsm + ((sizeof(LargeHead) + 15) & ~(size_t)15));   // (k, k) for k[R..n-1]
-   unsigned char *voff = reinterpret_cast<unsigned char *>(kh2 + HA_MAX_PATCH_R + 1);
-   float *B = reinterpret_cast<float *>(voff + ((HA_PATCH_PX + 15) & ~15));                      // [82][82]; first the column table
+   float *B = reinterpret_cast<float *>(kh2 + HA_MAX_PATCH_R + 1);                              // [82][82]; first the column table
    float *rowbuf = B + LG_B + 4;                                                                // band of row pairs; later patch / acc
    float4 *ctab = reinterpret_cast<float4 *>(B);
    float2 *v01 = reinterpret_cast<float2 *>(B);
@@ -117,13 +117,17 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
             const float wx = x + (float)ii * a11, fl = floorf(wx), fx = wx - fl;
             ctab[t] = make_float4(__int_as_float((int)fl), fx, 1.0f - fx, (float)ii * a21);
          }
-      const int RS2 = P + 2 * R + 2;                                  // float2 per padded row pair: R + P + R (+1 read past the last tap) + 1
-      const int G2 = max(1, min(32, rowbuf_floats / (2 * RS2)));      // row pairs per band
+      const int RS2 = (P + 2 * R + 2) | 1;                            // float2 per padded row pair: R + P + R (+1 read past the last tap) + 1, odd
+      // row pairs per band: 16 if they fit, else a power of two (the row pass maps lanes to row pairs)
+      const int G2fit = max(1, min(16, rowbuf_floats / (2 * RS2)));
+      const int lgLR = min(4, 31 - __clz(G2fit)), LR = 1 << lgLR, LJ = 32 >> lgLR;   // LR <= 16: two lanes share a 16-byte store
+      const int G2 = LR;
       float2 *rb2 = reinterpret_cast<float2 *>(rowbuf);
       const float invP = 1.0f / (float)P;
       __syncthreads();
       for (int r0 = 0; r0 < P; r0 += 2 * G2) {
          const int nrp = min(G2, (P - r0 + 1) >> 1);
+         const int nrb = (nrp + LR - 1) >> lgLR, njb = (HA_PATCH + LJ - 1) / LJ;
          // ---- sampling: item = (row pair, column) ---------------------------------------------------------------------
          for (int t = tid; t < nrp * P; t += NT) {
             const int rp = ha_fast_div(t, invP), xx = t - rp * P;
@@ -163,9 +167,14 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
          }
          __syncthreads();
          // ---- row pass: item = (row pair, pair of adjacent needed columns x0, x0+1); the tap windows overlap in all but
-         // one sample; chain order of every output is the reference's (left to right) ---------------------------------------
-         for (int t = tid; t < nrp * HA_PATCH; t += NT) {
-            const int rp = t / HA_PATCH, jx = t - rp * HA_PATCH;
+         // one sample; chain order of every output is the reference's (left to right).  Lanes run over ROW PAIRS (LR of
+         // them, RS2 odd: every 8-byte access of a half-warp in its own bank pair) and LJ = 32 / LR column pairs; the tap
+         // is the same for every lane (one broadcast read). ---------------------------------------------------------------
+         for (int u = tid >> 5; u < nrb * njb; u += NT / 32) {
+            const int ub = u / nrb;
+            const int rp_ = (u - ub * nrb) * LR + (tid & (LR - 1)), jx_ = ub * LJ + ((tid & 31) >> lgLR);
+            const bool live = rp_ < nrp && jx_ < HA_PATCH;
+            const int rp = min(rp_, nrp - 1), jx = min(jx_, HA_PATCH - 1);
             const ha_f2 *p = reinterpret_cast<const ha_f2 *>(rb2 + rp * RS2 + sh.rs_i[jx]);   // tap 0 of column x0 = padded column x0
             const ha_f2 *kc = reinterpret_cast<const ha_f2 *>(kh2) + R;                       // k(i) = kh[|i - R|]
             ha_f2 e = p[1];
@@ -187,19 +196,30 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
                e = *p++;
                b = ha_f2_fma(e, c, b);
             }
+            // fa = (row 2rp, row 2rp+1) of column x0, fb of column x0+1.  The lane LR further on holds the next column pair
+            // of the same rows: even column pairs take over row 2rp, odd ones row 2rp+1, and store 16 bytes each
             const float2 fa = ha_f2_unpack(a), fb = ha_f2_unpack(b);
+            const bool oddj = (jx_ & 1) != 0;
+            const float rx = __shfl_xor_sync(0xffffffffu, oddj ? fa.x : fa.y, LR);
+            const float ry = __shfl_xor_sync(0xffffffffu, oddj ? fb.x : fb.y, LR);
+            if (!live) continue;
             const int ja = r0 + 2 * rp;
-            float *d = T + (size_t)(R + ja) * 82 + 2 * jx;
-            const float2 oa = make_float2(fa.x, fb.x), ob = make_float2(fa.y, fb.y);
-            *reinterpret_cast<float2 *>(d) = oa;
-            if (ja + 1 < P) *reinterpret_cast<float2 *>(d + 82) = ob;
-            // BORDER_REPLICATE of the column pass: R copies of the first / last filtered row
-            if (ja == 0)
-               for (int k = 1; k <= R; k++) *reinterpret_cast<float2 *>(d - (size_t)k * 82) = oa;
-            if (ja + 1 >= P - 1) {
-               const float2 ol = (ja + 1 < P) ? ob : oa;
-               float *dl = T + (size_t)(R + P - 1) * 82 + 2 * jx;
-               for (int k = 1; k <= R; k++) *reinterpret_cast<float2 *>(dl + (size_t)k * 82) = ol;
+            if (jx_ == HA_PATCH - 1) {             // the last column pair has no partner
+               float *d = T + (size_t)(R + ja) * LG_TS + 2 * jx;
+               const float2 oa = make_float2(fa.x, fb.x);
+               *reinterpret_cast<float2 *>(d) = oa;
+               if (ja + 1 < P) *reinterpret_cast<float2 *>(d + LG_TS) = make_float2(fa.y, fb.y);
+               // BORDER_REPLICATE of the column pass: R copies of the first / last filtered row
+               if (ja == 0) for (int k = 1; k <= R; k++) *reinterpret_cast<float2 *>(d - (size_t)k * LG_TS) = oa;
+               if (ja == P - 1) for (int k = 1; k <= R; k++) *reinterpret_cast<float2 *>(d + (size_t)k * LG_TS) = oa;
+            } else if (!oddj) {
+               float *d = T + (size_t)(R + ja) * LG_TS + 2 * jx;
+               const float4 o = make_float4(fa.x, fb.x, rx, ry);
+               *reinterpret_cast<float4 *>(d) = o;
+               if (ja == 0) for (int k = 1; k <= R; k++) *reinterpret_cast<float4 *>(d - (size_t)k * LG_TS) = o;
+               if (ja == P - 1) for (int k = 1; k <= R; k++) *reinterpret_cast<float4 *>(d + (size_t)k * LG_TS) = o;
+            } else if (ja + 1 < P) {
+               *reinterpret_cast<float4 *>(T + (size_t)(R + ja + 1) * LG_TS + 2 * (jx - 1)) = make_float4(rx, ry, fa.y, fb.y);
             }
          }
          __syncthreads();
@@ -208,14 +228,14 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
       // serves both rows.  centre*k0, then (above + below) FMA'd outwards, as the reference. -----------------------------
       for (int t = tid; t < HA_PATCH * HA_PATCH; t += NT) {
          const int jy = t / HA_PATCH, q2 = t - jy * HA_PATCH;
-         const ha_f2 *base = reinterpret_cast<const ha_f2 *>(T + (size_t)(R + sh.rs_i[jy]) * 82 + 2 * q2);
+         const ha_f2 *base = reinterpret_cast<const ha_f2 *>(T + (size_t)(R + sh.rs_i[jy]) * LG_TS + 2 * q2);
          const ha_f2 *kc = reinterpret_cast<const ha_f2 *>(kh2);
-         ha_f2 am = base[0], bm = base[41];                        // T[yy - (k-1)], T[yy + 1 + (k-1)]
+         ha_f2 am = base[0], bm = base[LG_TS / 2];                        // T[yy - (k-1)], T[yy + 1 + (k-1)]
          ha_f2 acc0 = ha_f2_mul(am, kc[0]), acc1 = ha_f2_mul(bm, kc[0]);
-         const ha_f2 *up = base, *dn = base + 41;
+         const ha_f2 *up = base, *dn = base + LG_TS / 2;
 #pragma unroll 4
          for (int k = 1; k <= R; k++) {
-            up -= 41; dn += 41;
+            up -= LG_TS / 2; dn += LG_TS / 2;
             const ha_f2 ak = *up, bk = *dn, w = kc[k];
             acc0 = ha_f2_fma(ha_f2_add(ak, bm), w, acc0);         // row yy  : T[yy-k] + T[yy+k]
             acc1 = ha_f2_fma(ha_f2_add(am, bk), w, acc1);         // row yy+1: T[yy+1-k] + T[yy+1+k]
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
          ha_sift_describe<NT>([&](int jj, int ii) {
             const float *p = B + (2 * jj) * 82 + 2 * ii;
             return ha_bilinear(p[0], p[1], p[82], p[83], sh.rs_f[ii], sh.rs_f[jj]);
-         }, sh.red, patch, v01, voff, acc, tb, cand.desc + (size_t)i * 128, dump_normalized ? nullptr : dump, dump_normalized ? dump : nullptr);
+         }, sh.red, patch, v01, acc, tb, cand.desc + (size_t)i * 128, dump_normalized ? nullptr : dump, dump_normalized ? dump : nullptr);
       }
       if (tid == 0) cand.flags[i] |= HA_F_DESC;
    }
@@ -244,15 +264,15 @@ static int large_row_stride(int maxP)
    const float sigma = 1.5f * ((float)maxP / (float)HA_PATCH);
    int n = (int)(2.0 * 3.0 * sigma + 1.0);
    if (n % 2 == 0) n++;
-   return maxP + 2 * (n / 2) + 2;
+   return (maxP + 2 * (n / 2) + 2) | 1;
 }
 static int large_rowbuf_floats(int maxP) { return std::max(6144, 2 * large_row_stride(maxP) + 8); }
 // rows of the row-filtered scratch plane T per CTA: R + P + R
-size_t ha_describe_scratch_floats(int maxP) { return (size_t)(large_row_stride(maxP) + 2) * 82; }
+size_t ha_describe_scratch_floats(int maxP) { return (size_t)(large_row_stride(maxP) + 2) * LG_TS; }
 
 static int large_smem_bytes(int maxP)
 {
-   return (int)(((sizeof(LargeHead) + 15) & ~(size_t)15) + sizeof(float2) * (HA_MAX_PATCH_R + 1) + ((HA_PATCH_PX + 15) & ~15) +
+   return (int)(((sizeof(LargeHead) + 15) & ~(size_t)15) + sizeof(float2) * (HA_MAX_PATCH_R + 1) +
                 sizeof(float) * (LG_B + 4 + (size_t)large_rowbuf_floats(maxP)));
 }
 
