@@ -26,7 +26,7 @@ HESSIAN_DARK, HESSIAN_BRIGHT, HESSIAN_SADDLE = 0, 1, 2   # pyramid.h:51-55
 
 EXPORTED_SYMBOLS = [
     "hesaff_abi_version", "hesaff_last_error", "hesaff_params_default", "hesaff_create", "hesaff_destroy",
-    "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_detect_rgb8", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
+    "hesaff_detect_u8", "hesaff_detect_f32", "hesaff_detect_rgb8", "hesaff_pnm_info", "hesaff_detect_pnm", "hesaff_match_descriptors", "hesaff_result_counts", "hesaff_result_total", "hesaff_result_keypoints",
     "hesaff_result_keypoints_device", "hesaff_set_host_output", "hesaff_result_ellipses", "hesaff_result_detections", "hesaff_debug_geometry",
     "hesaff_debug_octave_size", "hesaff_debug_plane", "hesaff_debug_patches", "hesaff_launch_count",
     "hesaff_set_profiling", "hesaff_stage_times_ms", "hesaff_blur_time_ms", "hesaff_write_sift_file",
@@ -192,6 +192,21 @@ class AffineHessianDetector:
             ptr, ist = a.ctypes.data, rp * h   # C-contiguous (a[None] reports a zero stride for the new axis)
             self._keep = a
         _check(fn(self._h, C.c_void_p(ptr), n, w, h, rp, ist, on_device, C.c_void_p(stream or 0)))
+        self.n_images = n
+        self.n_detected = np.zeros(n, np.int32)
+        self.n_described = np.zeros(n, np.int32)
+        _check(lib().hesaff_result_counts(self._h, self.n_detected.ctypes.data, self.n_described.ctypes.data))
+        return self
+
+    def detectFiles(self, files, stream=None):
+        """`files`: list of bytes objects (or paths) holding binary PNM files of one size -- the pixel payload goes to
+        the GPU as it lies in the file, the gray conversion of hesaff.cpp:137-148 runs there (hesaff_detect_pnm)."""
+        blobs = [open(f, "rb").read() if isinstance(f, str) else bytes(f) for f in files]
+        n = len(blobs)
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p) for b in blobs])
+        sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+        self._keep = blobs
+        _check(lib().hesaff_detect_pnm(self._h, ptrs, sizes, n, C.c_void_p(stream or 0)))
         self.n_images = n
         self.n_detected = np.zeros(n, np.int32)
         self.n_described = np.zeros(n, np.int32)

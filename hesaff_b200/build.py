@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # HESAFF_LIB selects another build of the same library (tuning experiments: tools/build_variants.py)
 LIB = os.environ.get("HESAFF_LIB") or os.path.join(HERE, "libhesaff_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu", "describe.cu", "describe_large.cu", "export.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "blur_tma.cu", "keypoints.cu", "describe.cu", "describe_large.cu", "match.cu", "export.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "describe.cuh"), os.path.join(HERE, "..", "include", "hesaff_b200.h")]
 
 NVCC_FLAGS = [

@@ -139,18 +139,6 @@ static void gauss_kernel(int n, double sigma, std::vector<float> &k)
    for (int i = 0; i <= R; i++) k[i] = k[n - 1 - i] = (float)(v[i] * m);
 }
 
-static int make_taps(float sigma, Taps &t)
-{
-   const int n = blur_size(sigma);
-   if (n > HA_MAX_TAPS) return -1;
-   std::vector<float> k;
-   gauss_kernel(n, (double)sigma, k);
-   t.n = n;
-   memset(t.k, 0, sizeof(t.k));
-   for (int i = 0; i < n; i++) t.k[i] = k[i];
-   return 0;
-}
-
 // computeGaussMask, helpers.cpp:104-129
 static void smm_mask(float *mask, int size)
 {
@@ -244,6 +232,22 @@ template <typename T> static int upload(hesaff_ctx *c, const std::vector<T> &h, 
    return HESAFF_OK;
 }
 
+static int make_taps(hesaff_ctx *c, float sigma, Taps &t)
+{
+   const int n = blur_size(sigma);
+   std::vector<float> k;
+   gauss_kernel(n, (double)sigma, k);
+   t.n = n;
+   t.dk = nullptr;
+   memset(t.k, 0, sizeof(t.k));
+   if (n <= HA_MAX_TAPS) {
+      for (int i = 0; i < n; i++) t.k[i] = k[i];
+      return HESAFF_OK;
+   }
+   // more taps than the tiled kernels take by value: the generic kernels read them from device memory
+   return upload(c, k, &t.dk);
+}
+
 static int build_tables(hesaff_ctx *c)
 {
    std::vector<float> m19(HA_SMM_PX), m41(HA_PATCH_PX);
@@ -300,7 +304,7 @@ static int build_tables(hesaff_ctx *c)
       pn[m] = n;
       poff[m] = (int)pk.size();
       for (int i = n / 2; i < n; i++) pk.push_back(k[i]);
-      if (n / 2 > HA_MAX_PATCH_R) return fail(HESAFF_ERR_INVALID, "image too large: the per-patch blur would need more than 1039 taps (sqrt(W*H) must stay below ~4600)");
+      if (n / 2 > HA_MAX_PATCH_R) return fail(HESAFF_ERR_INVALID, "image too large: the per-patch blur would need more than 2079 taps (sqrt(W*H) must stay below ~9200)");
    }
    c->tables.pk_count = count;
    {  // fixed-stride copy for the shared-memory bins (P0 <= 93: m <= 46, R <= 10)
@@ -371,7 +375,10 @@ static int plan_geometry(const hesaff_params &p, int W, int H, Geom &g)
 
 static size_t per_image_bytes(const Geom &g, int max_cand)
 {
-   return g.arena_stride * 4 + (size_t)g.W * g.H + g.mask_stride * 8 + g.map_stride * 4 + (size_t)max_cand * 260;
+   // arena + host-input staging (up to 4 bytes per pixel) + candidate mask and its scan + octaveMap + candidate pool (SoA state,
+   // descriptors, work lists) + the output records of the call (hesaff_keypoint + ellipse for half the candidates)
+   return g.arena_stride * 4 + (size_t)g.W * g.H * 4 + g.mask_stride * 8 + g.map_stride * 4 + (size_t)max_cand * 260 +
+          (size_t)(max_cand / 2) * (sizeof(hesaff_keypoint) + 20);
 }
 
 template <typename T> static int dmalloc(T **p, size_t n)
@@ -447,7 +454,8 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    if (p->number_of_scales < 1 || p->number_of_scales + 2 > HA_MAX_LVL) return fail(HESAFF_ERR_INVALID, "number_of_scales out of range [1,12]");
    if (p->border < 2) return fail(HESAFF_ERR_INVALID, "border must be >= 2 (pyramid.cpp:208)");
    if (p->max_iter < 1) return fail(HESAFF_ERR_INVALID, "max_iter must be >= 1");
-   if (max_width < 1 || max_height < 1 || max_width >= (1 << 20) || max_height >= (1 << 20)) return fail(HESAFF_ERR_INVALID, "bad max size");
+   if (max_width < 1 || max_height < 1 || max_width >= (1 << 20) || max_height > 65535)
+      return fail(HESAFF_ERR_INVALID, "bad max size (width < 2^20, height <= 65535: rows index the y dimension of the launch grids)");
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       return fail(HESAFF_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -474,7 +482,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
       c->taps0.n = 0;
       if (p->initial_sigma > curSigma0) {
          float sigma = sqrtf(p->initial_sigma * p->initial_sigma - curSigma0 * curSigma0);
-         if (make_taps(sigma, c->taps0)) return fail(HESAFF_ERR_INVALID, "initial blur needs more than 33 taps");
+         { int rc = make_taps(c, sigma, c->taps0); if (rc) return rc; }
       }
       const int S = p->number_of_scales;
       float sigmaStep = powf(2.0f, 1.0f / (float)S);
@@ -483,7 +491,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
       c->lvl_sigma[0] = curSigma;
       for (int i = 1; i < S + 2; i++) {
          float sigma = curSigma * sqrtf(sigmaStep * sigmaStep - 1.0f);
-         if (make_taps(sigma, c->taps[i])) return fail(HESAFF_ERR_INVALID, "a pyramid blur needs more than 33 taps");
+         { int rc = make_taps(c, sigma, c->taps[i]); if (rc) return rc; }
          sigma = curSigma * sigmaStep;
          c->norm[i] = sigma * sigma;
          curSigma *= sigmaStep;
@@ -506,6 +514,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    // work-list entries carry the candidate index in 26 bits (describe.cu): at most 2^26 candidates per chunk
    if ((size_t)c->max_cand_per_image > (1ull << 26)) return fail(HESAFF_ERR_INVALID, "candidate pool of one image exceeds 2^26");
    chunk = (int)std::min<size_t>((size_t)chunk, (1ull << 26) / (size_t)c->max_cand_per_image);
+   chunk = std::min(chunk, 65535);    // the image index is the z dimension of the launch grids and 16 bits of the candidate key
    c->n_lanes = 2;
    if ((size_t)chunk * pib * 2 > free_b * 0.85) c->n_lanes = 1;
    if ((size_t)chunk * pib * c->n_lanes > free_b * 0.9) return fail(HESAFF_ERR_CUDA, "not enough device memory for max_batch images of this size");
@@ -583,11 +592,13 @@ static int flush_lane_output(hesaff_ctx *c, Lane &L)
 
 enum InFmt { IN_U8 = 0, IN_F32 = 1, IN_RGB8 = 2 };
 
+// `ptrs` (optional, host input only): image i starts at ptrs[i] instead of images + i * img_stride
 static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int W, int H, size_t row_pitch,
-                       size_t img_stride, int on_device, void *stream_)
+                       size_t img_stride, int on_device, void *stream_, const void *const *ptrs = nullptr)
 {
    if (!c) return fail(HESAFF_ERR_INVALID, "ctx is NULL");
-   if (!images || n < 0 || W < 1 || H < 1) return fail(HESAFF_ERR_INVALID, "bad image arguments");
+   if ((!images && !ptrs) || n < 0 || W < 1 || H < 1) return fail(HESAFF_ERR_INVALID, "bad image arguments");
+   if (ptrs && on_device) return fail(HESAFF_ERR_INVALID, "per-image pointers are for host input");
    if (W > c->max_w || H > c->max_h) return fail(HESAFF_ERR_INVALID, "image larger than the context was created for");
    const size_t esz = fmt == IN_U8 ? 1 : (fmt == IN_RGB8 ? 3 : 4);
    if (row_pitch < (size_t)W * esz || img_stride < row_pitch * (size_t)(H - 1) + (size_t)W * esz)
@@ -658,12 +669,21 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       c->last_chunks++;
       if (c->profiling) cudaEventRecord(L.ev[0], st);
       // ---- stage 0: upload + gray float image (hesaff.cpp:138-148) ---------------------------------
-      const char *src = (const char *)images + (size_t)start * img_stride;
+      const char *src = ptrs ? nullptr : (const char *)images + (size_t)start * img_stride;
       const void *dsrc = src;
       size_t d_row_pitch = row_pitch, d_img_stride = img_stride;
       if (!on_device) {
          d_row_pitch = (size_t)W * esz; d_img_stride = d_row_pitch * H;
-         if (row_pitch == d_row_pitch && img_stride == d_img_stride)
+         if (ptrs) {
+            for (int i = 0; i < cn; i++) {
+               const char *pi = (const char *)ptrs[start + i];
+               if (row_pitch == d_row_pitch)
+                  CK(cudaMemcpyAsync(L.stage_u8 + (size_t)i * d_img_stride, pi, d_img_stride, cudaMemcpyHostToDevice, st));
+               else
+                  CK(cudaMemcpy2DAsync(L.stage_u8 + (size_t)i * d_img_stride, d_row_pitch, pi, row_pitch, d_row_pitch, H,
+                                       cudaMemcpyHostToDevice, st));
+            }
+         } else if (row_pitch == d_row_pitch && img_stride == d_img_stride)
             CK(cudaMemcpyAsync(L.stage_u8, src, d_img_stride * cn, cudaMemcpyHostToDevice, st));
          else
             for (int i = 0; i < cn; i++)
@@ -697,7 +717,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
                                c->taps0, cn, st, c->lc))
                return fail(HESAFF_ERR_INVALID, "unsupported blur size");
          } else {
-            Taps id; id.n = 1; memset(id.k, 0, sizeof(id.k)); id.k[0] = 1.0f;   // firstLevel = image.clone()
+            Taps id; id.n = 1; id.dk = nullptr; memset(id.k, 0, sizeof(id.k)); id.k[0] = 1.0f;   // firstLevel = image.clone()
             ha_launch_blur(img_plane, L00, R00, nullptr, g.w[0], g.h[0], g.pitch[0], 0, 0, 0, g.arena_stride, c->norm[0], id,
                            cn, st, c->lc);
          }
@@ -817,6 +837,70 @@ extern "C" int hesaff_detect_rgb8(hesaff_ctx *ctx, const uint8_t *images, int n,
                                   size_t image_stride_bytes, int on_device, void *stream)
 {
    return detect_impl(ctx, images, IN_RGB8, n, width, height, row_pitch_bytes, image_stride_bytes, on_device, stream);
+}
+
+// ---- binary PNM files: header on the host, pixels on the device (the step before the path, hesaff.cpp:137-148) ---------
+// Parses the header of a binary PNM ("P5" gray / "P6" colour, maxval 255; '#' comments allowed) held in memory.
+extern "C" int hesaff_pnm_info(const void *file, size_t bytes, int *width, int *height, int *channels, size_t *data_offset)
+{
+   const unsigned char *p = (const unsigned char *)file;
+   if (!p || bytes < 7 || p[0] != 'P' || (p[1] != '5' && p[1] != '6')) return fail(HESAFF_ERR_INVALID, "not a binary PNM (P5/P6) file");
+   size_t pos = 2;
+   long vals[3] = {0, 0, 0};
+   for (int got = 0; got < 3;) {
+      if (pos >= bytes) return fail(HESAFF_ERR_INVALID, "truncated PNM header");
+      const unsigned char ch = p[pos];
+      if (ch == '#') { while (pos < bytes && p[pos] != '\n') pos++; continue; }
+      if (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r' || ch == '\v' || ch == '\f') { pos++; continue; }
+      if (ch < '0' || ch > '9') return fail(HESAFF_ERR_INVALID, "bad PNM header");
+      long v = 0;
+      while (pos < bytes && p[pos] >= '0' && p[pos] <= '9') { v = v * 10 + (p[pos] - '0'); pos++; if (v > (1l << 30)) return fail(HESAFF_ERR_INVALID, "bad PNM header"); }
+      vals[got++] = v;
+   }
+   pos++;   // the single whitespace byte after maxval
+   const int ch = p[1] == '5' ? 1 : 3;
+   if (vals[0] <= 0 || vals[1] <= 0 || vals[2] != 255) return fail(HESAFF_ERR_INVALID, "PNM: only maxval 255 is supported");
+   if (pos > bytes || bytes - pos < (size_t)vals[0] * (size_t)vals[1] * (size_t)ch) return fail(HESAFF_ERR_INVALID, "truncated PNM pixel data");
+   if (width) *width = (int)vals[0];
+   if (height) *height = (int)vals[1];
+   if (channels) *channels = ch;
+   if (data_offset) *data_offset = pos;
+   return HESAFF_OK;
+}
+
+extern "C" int hesaff_detect_pnm(hesaff_ctx *ctx, const void *const *files, const size_t *file_bytes, int n, void *stream)
+{
+   if (!ctx || !files || !file_bytes || n < 1) return fail(HESAFF_ERR_INVALID, "bad arguments");
+   std::vector<const void *> pix((size_t)n);
+   int W = 0, H = 0, CH = 0;
+   for (int i = 0; i < n; i++) {
+      int w, h, ch;
+      size_t off;
+      const int rc = hesaff_pnm_info(files[i], file_bytes[i], &w, &h, &ch, &off);
+      if (rc) return rc;
+      if (i == 0) { W = w; H = h; CH = ch; }
+      else if (w != W || h != H || ch != CH) return fail(HESAFF_ERR_INVALID, "the files of one call must have the same size and type");
+      pix[i] = (const char *)files[i] + off;
+   }
+   // the pixel payload is handed to the copy engine as it lies in the file; P6 is converted to gray on the GPU
+   return detect_impl(ctx, nullptr, CH == 1 ? IN_U8 : IN_RGB8, n, W, H, (size_t)W * CH, (size_t)W * CH * H, 0, stream, pix.data());
+}
+
+// ---- consumer of the records: descriptor matching (match.cu) ----------------------------------------------------------
+extern "C" int hesaff_match_descriptors(int device, const hesaff_keypoint *d_query, size_t n_query, const hesaff_keypoint *d_db,
+                                        size_t n_db, int32_t *d_best_index, uint32_t *d_best_dist2, uint32_t *d_second_dist2,
+                                        void *stream)
+{
+   if ((n_query && !d_query) || (n_db && !d_db) || !d_best_index || !d_best_dist2) return fail(HESAFF_ERR_INVALID, "NULL argument");
+   if (n_query > 0xffffffffull || n_db > 0x7fffffffull) return fail(HESAFF_ERR_INVALID, "too many records");
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(HESAFF_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+   if (device < 0 || device >= ndev) return fail(HESAFF_ERR_INVALID, "bad device index");
+   CK(cudaSetDevice(device));
+   ha_launch_match(d_query, (uint32_t)n_query, d_db, (uint32_t)n_db, d_best_index, d_best_dist2, d_second_dist2, (cudaStream_t)stream);
+   CK(cudaGetLastError());
+   CK(cudaStreamSynchronize((cudaStream_t)stream));
+   return HESAFF_OK;
 }
 
 // ---- results -------------------------------------------------------------------------------------------

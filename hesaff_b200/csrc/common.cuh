@@ -18,7 +18,7 @@
 #define HA_SMM 19              // SMM window side (affine.h:43)
 #define HA_SMM_PX (HA_SMM * HA_SMM)
 
-#define HA_MAX_PATCH_R 519     // largest half-width of a per-patch blur kernel (shared-memory table)
+#define HA_MAX_PATCH_R 1039    // largest half-width of a per-patch blur kernel (shared-memory table of the LARGE bin): sqrt(W*H) <~ 9200
 
 #ifndef HA_BIN_TINY_MAXP
 #define HA_BIN_TINY_MAXP 39    // patch+SIFT kernel bins by source-patch side P
@@ -30,7 +30,8 @@
 
 struct Taps {
    int n;
-   float k[HA_MAX_TAPS];
+   float k[HA_MAX_TAPS];      // the taps when n <= HA_MAX_TAPS (passed to the kernels by value)
+   const float *dk;           // device copy of all n taps; the generic kernels use it when n > HA_MAX_TAPS
 };
 
 // Geometry of the pyramid of one image and the offsets of every plane inside the per-image arena.
@@ -186,4 +187,6 @@ void ha_launch_compact(Cand cand, const uint32_t *count, uint32_t cap, const uin
 void ha_launch_export_detections(Cand cand, const uint32_t *count, uint32_t cap, const uint32_t *det_off,
                                  const Geom *dg, hesaff_detection *out, cudaStream_t st, LaunchCounter &lc);
 int ha_describe_smem_bytes(int bin);
+void ha_launch_match(const hesaff_keypoint *query, uint32_t nq, const hesaff_keypoint *db, uint32_t ndb, int32_t *best_index,
+                     uint32_t *best_d2, uint32_t *second_d2, cudaStream_t st);
 size_t ha_describe_scratch_floats(int maxP);

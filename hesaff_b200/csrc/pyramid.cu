@@ -251,10 +251,71 @@ static int launch_blur_n(const BlurArgs &a, const Taps &taps, int n, cudaStream_
    return 0;
 }
 
+// ---- any number of taps (sigma is a free parameter of the reference, helpers.cpp:283-289: number_of_scales = 1 or a large
+// initial_sigma need more than HA_MAX_TAPS): one thread per pixel, taps from global memory, the same operation order as the
+// tiled kernels for n >= 7 (row: left-to-right FMA chain; column: centre first, then (above + below) outwards).  The row
+// pass writes into the response plane, which the Hessian pass overwrites afterwards.
+__global__ void k_blur_row_generic(const float *__restrict__ src, float *__restrict__ tmp, int W, int H, int pitch,
+                                   unsigned long long img_stride, const float *__restrict__ k, int n)
+{
+   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+   if (x >= W) return;
+   const size_t ioff = (size_t)blockIdx.z * img_stride + (size_t)y * pitch;
+   const float *row = src + ioff;
+   const int R = n >> 1;
+   float acc = row[max(x - R, 0)] * k[0];
+   for (int i = 1; i < n; i++) acc = __fmaf_rn(row[min(max(x - R + i, 0), W - 1)], k[i], acc);
+   tmp[ioff + x] = acc;
+}
+
+__global__ void k_blur_col_generic(const float *__restrict__ tmp, float *__restrict__ dst, int W, int H, int pitch,
+                                   unsigned long long img_stride, const float *__restrict__ k, int n)
+{
+   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+   if (x >= W) return;
+   const size_t ioff = (size_t)blockIdx.z * img_stride;
+   const float *col = tmp + ioff + x;
+   const int R = n >> 1;
+   float acc = col[(size_t)y * pitch] * k[R];
+   for (int i = 1; i <= R; i++)
+      acc = __fmaf_rn(col[(size_t)max(y - i, 0) * pitch] + col[(size_t)min(y + i, H - 1) * pitch], k[R + i], acc);
+   dst[ioff + (size_t)y * pitch + x] = acc;
+}
+
+// halfImage, helpers.cpp:331-339
+__global__ void k_half(const float *__restrict__ src, float *__restrict__ dst, int pitch, int hW, int hH, int hpitch,
+                       unsigned long long img_stride)
+{
+   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+   if (x >= hW || y >= hH) return;
+   const size_t ioff = (size_t)blockIdx.z * img_stride;
+   dst[ioff + (size_t)y * hpitch + x] = src[ioff + (size_t)(2 * y) * pitch + 2 * x];
+}
+
+static int launch_blur_generic(const float *src, float *dstL, float *dstR, float *half, int W, int H, int pitch, int hW, int hH,
+                               int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
+                               LaunchCounter &lc)
+{
+   if (!taps.dk || !dstR) return -1;
+   dim3 grid((W + 127) / 128, H, n);
+   k_blur_row_generic<<<grid, 128, 0, st>>>(src, dstR, W, H, pitch, img_stride, taps.dk, taps.n);
+   k_blur_col_generic<<<grid, 128, 0, st>>>(dstR, dstL, W, H, pitch, img_stride, taps.dk, taps.n);
+   lc.n += 2;
+   ha_launch_hessian(dstL, dstR, W, H, pitch, img_stride, norm, n, st, lc);
+   if (half) {
+      dim3 hg((hW + 127) / 128, hH, n);
+      k_half<<<hg, 128, 0, st>>>(dstL, half, pitch, hW, hH, hpitch, img_stride);
+      lc.n++;
+   }
+   return 0;
+}
+
 int ha_launch_blur(const float *src, float *dstL, float *dstR, float *half, int W, int H, int pitch, int hW, int hH,
                    int hpitch, unsigned long long img_stride, float norm, const Taps &taps, int n, cudaStream_t st,
                    LaunchCounter &lc)
 {
+   if (taps.n > HA_MAX_TAPS)
+      return launch_blur_generic(src, dstL, dstR, half, W, H, pitch, hW, hH, hpitch, img_stride, norm, taps, n, st, lc);
    static const bool use_tma = getenv("HESAFF_NO_TMA") == nullptr;
    if (use_tma && ha_launch_blur_tma(src, dstL, dstR, half, W, H, pitch, hW, hH, hpitch, img_stride, norm, taps, n, st) == 0) {
       lc.n++;

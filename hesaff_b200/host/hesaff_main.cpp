@@ -45,28 +45,17 @@ static double wallTime()
    return (double)ts.tv_sec + (double)ts.tv_nsec / 1.0e9;
 }
 
-// Reads P5/P6 with maxval 255. gray: h*w bytes when the file is P5; rgb non-empty when P6.
-static bool readPNM(const char *path, int &w, int &h, vector<unsigned char> &gray, vector<unsigned char> &rgb)
+// The whole file as it is on disk; the library parses the PNM header and the pixels go to the GPU untouched
+static bool readFile(const char *path, vector<char> &bytes)
 {
-   ifstream f(path, ios::binary);
+   ifstream f(path, ios::binary | ios::ate);
    if (!f) return false;
-   string magic;
-   f >> magic;
-   if (magic != "P5" && magic != "P6") return false;
-   int vals[3], got = 0;
-   while (got < 3 && f) {
-      int ch = f.peek();
-      if (ch == '#') { string line; getline(f, line); continue; }
-      if (isspace(ch)) { f.get(); continue; }
-      f >> vals[got++];
-   }
-   f.get();
-   if (got < 3 || vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0) return false;
-   w = vals[0]; h = vals[1];
-   vector<unsigned char> &dst = (magic == "P5") ? gray : rgb;
-   dst.resize((size_t)w * h * (magic == "P5" ? 1 : 3));
-   f.read((char *)dst.data(), dst.size());
-   return (size_t)f.gcount() == dst.size();
+   const streamsize n = f.tellg();
+   if (n <= 0) return false;
+   bytes.resize((size_t)n);
+   f.seekg(0);
+   f.read(bytes.data(), n);
+   return (streamsize)f.gcount() == n;
 }
 
 int main(int argc, char **argv)
@@ -97,23 +86,20 @@ int main(int argc, char **argv)
    int status = 0;
    for (size_t fi = 0; fi < files.size(); fi++) {
       int w = 0, h = 0;
-      vector<unsigned char> gray, rgb;
+      vector<char> file;
       vector<hesaff_keypoint> keys;
       int nDetected = 0, nAffine = 0;
       double t1 = 0, elapsed = 0;
       bool written = false;
-      if (readPNM(files[fi], w, h, gray, rgb)) {
+      if (readFile(files[fi], file) && hesaff_pnm_info(file.data(), file.size(), &w, &h, 0, 0) == HESAFF_OK) {
          hesaff_ctx *ctx = 0;
          int rc = hesaff_create(&ctx, &p, device, w, h, 1, 0);
          if (rc == HESAFF_OK) {
-            if (!rgb.empty()) {
-               // colour input: the gray conversion (float(c0)+c1+c2)/3.0f of hesaff.cpp:138-148 runs on the GPU
-               t1 = wallTime();
-               rc = hesaff_detect_rgb8(ctx, rgb.data(), 1, w, h, (size_t)3 * w, (size_t)3 * w * h, 0, 0);
-            } else {
-               t1 = wallTime();
-               rc = hesaff_detect_u8(ctx, gray.data(), 1, w, h, (size_t)w, (size_t)w * h, 0, 0);
-            }
+            // imread + the gray conversion (float(c0)+c1+c2)/3.0f of hesaff.cpp:137-148: header on the host, pixels on the GPU
+            const void *fp = file.data();
+            const size_t fb = file.size();
+            t1 = wallTime();
+            rc = hesaff_detect_pnm(ctx, &fp, &fb, 1, 0);
             if (rc == HESAFF_OK) {
                rc = hesaff_result_counts(ctx, &nDetected, &nAffine);
                keys.resize((size_t)hesaff_result_total(ctx));

@@ -91,3 +91,26 @@ def all_gather_keypoints(dist, torch, local_records, global_counts, starts, devi
         out[pos:pos + per_rank[r]] = recv[r, :per_rank[r]]
         pos += per_rank[r]
     return out
+
+
+def match_descriptors(torch, query, database, device):
+    """The consumer of the gathered records (README:49-53): nearest neighbour of every query record among the database
+    records by squared L2 distance over the 128 descriptor bytes, on the GPU (hesaff_match_descriptors).
+    query, database : [n, 164] uint8 CUDA tensors (e.g. device_records(...) and all_gather_keypoints(...)).
+    Returns (best_index int32 [nq], best_dist2 int32 [nq], second_dist2 int32 [nq]); -1 everywhere if the database is empty."""
+    import ctypes as C
+    from . import api
+    q = query.reshape(-1, RECORD_BYTES).contiguous()
+    d = database.reshape(-1, RECORD_BYTES).contiguous()
+    nq, nd = q.shape[0], d.shape[0]
+    idx = torch.empty(nq, dtype=torch.int32, device=device)
+    d1 = torch.empty(nq, dtype=torch.int32, device=device)
+    d2 = torch.empty(nq, dtype=torch.int32, device=device)
+    if nq == 0:
+        return idx, d1, d2
+    dev = torch.device(device)
+    torch.cuda.current_stream(dev).synchronize()      # the records may still be in flight on torch's stream
+    f = api.lib().hesaff_match_descriptors
+    f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    api._check(f(dev.index or 0, q.data_ptr(), nq, d.data_ptr() if nd else None, nd, idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), None))
+    return idx, d1, d2

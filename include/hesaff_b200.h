@@ -116,6 +116,21 @@ int hesaff_detect_f32(hesaff_ctx *ctx, const float *images, int n, int width, in
 int hesaff_detect_rgb8(hesaff_ctx *ctx, const uint8_t *images, int n, int width, int height, size_t row_pitch_bytes,
                        size_t image_stride_bytes, int on_device, void *stream);
 
+/* Image files as they are on disk (replaces cv::imread + the conversion loop, hesaff.cpp:137-148): `files[i]` points to the
+ * bytes of a binary PNM file (P5 gray or P6 colour, maxval 255) in host memory, `file_bytes[i]` is its length.  Only the
+ * header is parsed on the host; the pixel payload is uploaded untouched and the gray conversion runs on the GPU.  All files
+ * of one call must have the same width, height and type.  hesaff_pnm_info parses one header (any output may be NULL). */
+int hesaff_pnm_info(const void *file, size_t bytes, int *width, int *height, int *channels, size_t *data_offset);
+int hesaff_detect_pnm(hesaff_ctx *ctx, const void *const *files, const size_t *file_bytes, int n, void *stream);
+
+/* The consumer of the records (the step after the path, README:49-53: matching SIFT descriptors): for every query record the
+ * nearest database record by squared L2 distance over the 128 descriptor bytes (exact integer arithmetic; ties go to the
+ * lower index), that distance and the distance of the second nearest (Lowe's ratio test; may be NULL).  All pointers are
+ * DEVICE pointers on `device` -- e.g. hesaff_result_keypoints_device, or the records of every rank after the variable-size
+ * all-gather.  With n_db == 0 every index is -1 and the distances are 0xffffffff.  Synchronises `stream` before it returns. */
+int hesaff_match_descriptors(int device, const hesaff_keypoint *d_query, size_t n_query, const hesaff_keypoint *d_db,
+                             size_t n_db, int32_t *d_best_index, uint32_t *d_best_dist2, uint32_t *d_second_dist2, void *stream);
+
 /* ---- results of the last detect call ---------------------------------------------------------- */
 /* Per image: detections (g_numberOfPoints, hesaff.cpp:68) and described keypoints (g_numberOfAffinePoints /
  * keys.size(), hesaff.cpp:103).  Either pointer may be NULL.  Arrays of n ints. */

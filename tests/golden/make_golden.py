@@ -35,6 +35,9 @@ CASES = [  # name, w, h, seed, param overrides
     ("tex_333x251_s7", 333, 251, 7, {}),
     ("tex_640x480_s1_S10_oct3", 640, 480, 1, {"number_of_scales": 10, "max_octaves": 3}),
     ("tex_512x512_s5_thr5_oct6", 512, 512, 5, {"threshold": 5.0, "max_octaves": 6}),
+    # desc_factor 2: most keypoints have imageToPatchScale <= 0.4, the direct-sampling branch of normalizeAffine (affine.cpp:135-142)
+    ("tex_320x240_s11_df2", 320, 240, 11, {"desc_factor": 2.0}),
+    ("tex_320x240_s11_S1", 320, 240, 11, {"number_of_scales": 1}),
 ]
 
 
@@ -73,6 +76,8 @@ def main():
     ref = oracle.load("ref")
     os.makedirs(G, exist_ok=True)
     summary = {}
+    if "--no-full" in sys.argv and os.path.exists(os.path.join(G, "summary.json")):   # keep the full-frame entries
+        summary = {k: v for k, v in json.load(open(os.path.join(G, "summary.json"))).items() if k.startswith("full_")}
     for name, w, h, seed, over in CASES:
         img = textured(w, h, seed)
         d = ref.detect(img.astype(np.float32), ref.default_params(**over))

@@ -68,6 +68,8 @@ CASES = [
     (512, 512, 5, {"threshold": 5.0, "max_octaves": 6}),
     (97, 131, 22, {}),
     (40, 30, 25, {}),
+    (320, 240, 11, {"number_of_scales": 1}),     # second incremental blur: 35 taps -> the any-tap kernels (helpers.cpp:283-289)
+    (320, 240, 11, {"desc_factor": 2.0}),        # imageToPatchScale <= 0.4: normalizeAffine samples 41x41 directly (affine.cpp:135-142)
 ]
 
 
@@ -537,4 +539,114 @@ def test_full_1080p_frame_against_the_reference_build_directly(hb, ref_oracle):
     assert len(kw) > 36000
     st = compare_keypoints(det.keys(), kw, mr_size=det.par.desc_factor)
     assert st["aligned"] >= len(kw) - slack and st["within_tol_frac"] * len(kw) >= len(kw) - 2 * slack, st
+    det.close()
+
+
+# ---- the steps either side of the path ----------------------------------------------------------------------
+def test_pnm_files_go_to_the_gpu_as_they_are(hb):
+    """hesaff_detect_pnm (8(f) rank 2): raw P5 / P6 file bytes in, header parsed on the host, pixels converted on the GPU;
+    same records as the array entry points."""
+    g = np.stack([textured(200, 150, 61), textured(200, 150, 62)])
+    det = run(hb, g)
+    want = det.keys().tobytes()
+    p5 = [b"P5\n# a comment\n200 150\n255\n" + im.tobytes() for im in g]
+    det.detectFiles(p5)
+    assert det.keys().tobytes() == want and det.n_described.tolist() == [int(v) for v in det.n_described]
+    p6 = [b"P6 200 150 255\n" + np.repeat(im[:, :, None], 3, 2).tobytes() for im in g]      # gray stored as colour
+    det.detectFiles(p6)
+    assert det.keys().tobytes() == want
+    with pytest.raises(hb.HesaffError):
+        det.detectFiles([p5[0], b"P5\n100 150\n255\n" + bytes(100 * 150)])                   # mixed sizes
+    with pytest.raises(hb.HesaffError):
+        det.detectFiles([p5[0][:-10]])                                                       # truncated payload
+    det.close()
+
+
+def test_descriptor_matcher_is_exact(hb):
+    """hesaff_match_descriptors (8(f) rank 3, the consumer): nearest / second nearest by squared L2 over the 128 bytes
+    equal a numpy brute force, ties to the lower index."""
+    import torch
+    from hesaff_b200 import shard
+    a, b = textured(320, 240, 71), textured(320, 240, 71)
+    b = np.roll(b, 3, axis=1)                                 # the same texture shifted: many true matches
+    det = run(hb, np.stack([a, b]))
+    keys = det.keys()
+    off = det.offsets()
+    dev = torch.device("cuda:0")
+    rec = shard.device_records(torch, det, dev)
+    q, d = rec[off[0]:off[1]], rec[off[1]:off[2]]
+    idx, d1, d2 = (t.cpu().numpy() for t in shard.match_descriptors(torch, q, d, dev))
+    qa = keys["desc"][off[0]:off[1]].astype(np.int64)
+    da = keys["desc"][off[1]:off[2]].astype(np.int64)
+    dist = ((qa[:, None, :] - da[None, :, :]) ** 2).sum(2)
+    order = np.argsort(dist, axis=1, kind="stable")
+    assert np.array_equal(idx, order[:, 0])
+    assert np.array_equal(d1, dist[np.arange(len(qa)), order[:, 0]])
+    assert np.array_equal(d2, dist[np.arange(len(qa)), order[:, 1]])
+    # the shift is 3 px: most keypoints find their own copy (distance ratio test of Lowe)
+    good = d1 < 0.36 * d2
+    dx = keys["x"][off[1]:off[2]][idx[good]] - keys["x"][off[0]:off[1]][good]
+    assert good.sum() > 300 and np.mean(np.abs(dx - 3) < 0.5) > 0.9
+    i0, e1, _ = shard.match_descriptors(torch, q, rec[:0], dev)
+    assert (i0.cpu().numpy() == -1).all() and (e1.cpu().numpy() == -1).all()
+    det.close()
+
+
+TWO_RANK_WORKER = r'''
+import hashlib, json, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch
+import torch.distributed as dist
+import hesaff_b200 as hb
+from hesaff_b200 import shard
+from tools.gen_textured import textured
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+n = 5                                                           # uneven blocks: 3 + 2
+imgs = np.stack([textured(320, 240, 40 + s) for s in range(n)])
+starts = shard.partition(n, world)
+mine = imgs[starts[rank]:starts[rank + 1]]
+det = hb.AffineHessianDetector(hb.HessianAffineParams(), rank, 320, 240, max_batch=len(mine))
+det.detectPyramidKeypoints(mine)
+counts = shard.all_gather_counts(dist, torch, np.stack([det.n_detected, det.n_described], 1), dev)
+rec = shard.device_records(torch, det, dev)
+allrec = shard.all_gather_keypoints(dist, torch, rec, counts, starts, dev)      # 164-byte records over NVLink
+idx, d1, d2 = shard.match_descriptors(torch, rec, allrec, dev)                  # consumer: every local record finds itself
+off = shard.global_offsets(counts)
+self_index = np.arange(off[starts[rank]], off[starts[rank + 1]])
+out = {"rank": rank, "counts": counts.tolist(), "sha": hashlib.sha256(allrec.cpu().numpy().tobytes()).hexdigest(),
+       "self_match": bool((d1.cpu().numpy() == 0).all() and (idx.cpu().numpy() <= self_index).all()), "n_local": int(rec.shape[0])}
+print("RESULT " + json.dumps(out), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_equal_one_gpu_and_gather_over_nccl(hb, tmp_path):
+    """SURVEY App. C / 8(e),(f)3 on hardware: two ranks, each with its block of the batch on its own GPU; the concatenated
+    records (variable-size all-gather over nccl) are byte-identical to the single-GPU run, on every rank."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(TWO_RANK_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29800 + os.getpid() % 100), str(script), root], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = [json.loads(ln.split("RESULT ", 1)[1]) for ln in r.stdout.splitlines() if "RESULT " in ln]
+    assert sorted(x["rank"] for x in res) == [0, 1]
+    imgs = np.stack([textured(320, 240, 40 + s) for s in range(5)])
+    det = run(hb, imgs)
+    import hashlib
+    want = hashlib.sha256(det.keys().tobytes()).hexdigest()
+    for x in res:
+        assert x["sha"] == want and x["self_match"]
+        assert [c[1] for c in x["counts"]] == det.n_described.tolist() and [c[0] for c in x["counts"]] == det.n_detected.tolist()
+    assert sum(x["n_local"] for x in res) == det.total()
     det.close()

@@ -191,3 +191,25 @@ def test_count_all_gather_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_pnm_header_parser():
+    """hesaff_pnm_info is host-only (no GPU): P5/P6, comments, whitespace forms, and the error cases."""
+    import ctypes as C
+    import hesaff_b200
+    L = hesaff_b200.lib()
+    L.hesaff_pnm_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+
+    def info(b):
+        w, h, ch, off = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        rc = L.hesaff_pnm_info(b, len(b), C.byref(w), C.byref(h), C.byref(ch), C.byref(off))
+        return rc, w.value, h.value, ch.value, off.value
+
+    hdr = b"P5\n# made by a test\n  7 3\n#x\n255\n"
+    assert info(hdr + bytes(21)) == (0, 7, 3, 1, len(hdr))
+    assert info(b"P6 4 2 255 " + bytes(24)) == (0, 4, 2, 3, 11)
+    assert info(b"P6 4 2 255 " + bytes(23))[0] < 0            # truncated payload
+    assert info(b"P2 4 2 255 " + bytes(24))[0] < 0            # ASCII PNM is not supported
+    assert info(b"P5 4 2 65535 " + bytes(16))[0] < 0          # 16-bit
+    assert info(b"P5 4")[0] < 0 and info(b"")[0] < 0
+    assert b"PNM" in L.hesaff_last_error()

@@ -12,7 +12,6 @@
 #include <string>
 #include "../hesaff_b200/csrc/pyramid.cu"
 #include "../hesaff_b200/csrc/blur_tma.cu"
-#include "old/blur_v2.cuh"
 
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -23,7 +22,7 @@ static void gauss(int n, double sigma, Taps &t)
    double sum = 0;
    for (int i = 0; i < R; i++) { double x = i - R; v[i] = exp(-0.5 / (sigma * sigma) * x * x); sum += v[i]; }
    v[R] = 1; sum = 2 * sum + 1;
-   t.n = n; memset(t.k, 0, sizeof(t.k));
+   t.n = n; t.dk = nullptr; memset(t.k, 0, sizeof(t.k));
    for (int i = 0; i <= R; i++) t.k[i] = t.k[n - 1 - i] = (float)(v[i] / sum);
 }
 
@@ -87,7 +86,7 @@ int main(int argc, char **argv)
       }
       struct V { const char *name; int kind; int variant; };
 #define VV(oh, nw, minb, sh, se) (oh | (nw << 8) | (minb << 16) | (sh << 25) | (se << 26))
-      std::vector<V> vs = {{"v1 k_blur (no TMA)", 1, 0}, {"v2 k_blur_v2 (r1b)", 2, 0}, {"v3 default", 3, 0},
+      std::vector<V> vs = {{"v1 k_blur (no TMA)", 1, 0}, {"v3 default", 3, 0},
                            {"v3 oh40 x4 noshfl", 3, VV(40, 8, 4, 1, 0)}, {"v3 oh40 x4", 3, VV(40, 8, 4, 1, 1)},
                            {"v3 oh48 x3", 3, VV(48, 8, 3, 1, 1)}, {"v3 oh56 x3", 3, VV(56, 8, 3, 1, 1)}, {"v3 oh56 x2", 3, VV(56, 8, 2, 1, 1)},
                            {"v3 oh56 x2 noshfl", 3, VV(56, 8, 2, 1, 0)}};
@@ -104,7 +103,6 @@ int main(int argc, char **argv)
                }
                return -1;
             }
-            if (v.kind == 2) return ha_launch_blur_v2(src, L, Rp, Hp, W, H, pitch, hW, hH, hpitch, istride, norm, t, n, 0);
             return ha_launch_blur_tma(src, L, Rp, Hp, W, H, pitch, hW, hH, hpitch, istride, norm, t, n, 0, v.variant);
          };
          CKB(cudaMemset(L, 0xFF, total * 4)); CKB(cudaMemset(Rp, 0xFF, total * 4)); CKB(cudaMemset(Hp, 0, total * 4));
