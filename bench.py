@@ -141,10 +141,13 @@ def _cpu_worker(args):
     return time.perf_counter() - t, int(len(d)), int(d["described"].sum())
 
 
+NCU_TRAFFIC_FILE = "profiles/r2_k_blur_tma_ncu.txt"     # first launch listed = octave 0, 11 taps, 32 x 1920x1080
+
+
 def ncu_traffic():
     """DRAM bytes (read+write) of one octave-0 k_blur_tma launch from the committed `ncu --set full` capture
-    (profiles/r1d_k_blur_tma_ncu.txt), with the algorithmic bytes of the same launch."""
-    path = os.path.join(ROOT, "profiles", "r1b_k_blur_tma_ncu.txt")
+    (NCU_TRAFFIC_FILE), with the algorithmic bytes of the same launch."""
+    path = os.path.join(ROOT, NCU_TRAFFIC_FILE)
     try:
         rd = wr = None
         for line in open(path):
@@ -187,7 +190,8 @@ def cpu_reference_run(images_u8, over, cores):
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(min(cores, n)) as pool:
-        res = pool.map(_cpu_worker, [(kind, images_u8[i].tobytes(), h, w, over) for i in range(n)], chunksize=1)
+        res = pool.map(_cpu_worker, [(kind, images_u8[i].tobytes(), h, w, over) for i in range(n)],
+                       chunksize=max(1, n // min(cores, n)))
     wall = time.perf_counter() - t0
     return {"kind": "reference" if kind == "ref" else "port", "wall_s": wall, "images": n, "mpix": n * h * w / 1e6,
             "single_core_s_per_image": statistics.mean(r[0] for r in res), "detections": [r[1] for r in res],
@@ -207,7 +211,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="batch1024_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
-    ap.add_argument("--cpu-images", type=int, default=0, help="CPU sample size (default: three images per host core, <= 192)")
+    ap.add_argument("--cpu-images", type=int, default=0, help="CPU sample size (default: 16 images per worker process for the cpu_baseline leg, BASELINE.md 3.3; 8 per timed step of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -235,19 +239,24 @@ def main():
             return 0
         import torch
         from tools.gen_textured import textured
-        n_cpu = args.cpu_images or min(3 * host_cores, 192)   # ~10-20 s of host work per step
+        # every timed step: 8 images per worker process (about 30 s of host work at 1080p); warm-up steps: one per process
+        per_proc = 8 if W * H <= 1920 * 1080 else (2 if W * H <= 3840 * 2160 else 1)
+        n_cpu = args.cpu_images or min(per_proc * host_cores, 512)
         if torch.cuda.is_available():
             imgs = synth_textured_gpu(torch, n_cpu, H, W, 1234, "cuda:0").cpu().numpy()
         else:
             imgs = np.stack([textured(W, H, 1000 + i) for i in range(min(n_cpu, 8))])
         times = []
         for it in range(args.warmup + args.steps):
+            if it < args.warmup:
+                cpu_reference_run(imgs[:min(host_cores, imgs.shape[0])], over, host_cores)
+                continue
             r = cpu_reference_run(imgs, over, host_cores)
-            if it >= args.warmup:
-                times.append(r["wall_s"])
+            times.append(r["wall_s"])
         t = sum(times) / len(times)
         v = imgs.shape[0] * H * W / 1e6 / t
-        sample = "%d images of the workload per step, one per worker process, %d processes" % (imgs.shape[0], r["workers"])
+        sample = "%d images of the workload per timed step, %d worker processes (one per physical core), %.1f images per process" % (
+            imgs.shape[0], r["workers"], imgs.shape[0] / r["workers"])
         print(json.dumps({
             "impl": "reference", "metric": "Mpixels/sec end-to-end (detect+affine+SIFT)", "value": v, "unit": "Mpix/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
@@ -369,6 +378,8 @@ def main():
         blur_ms = stage[6] / args.steps
         n_blur_launches = int(round(stage[7] / args.steps))
         achieved = blur_bytes * batch / (blur_ms / 1e3) / 1e9 if blur_ms > 0 else 0.0
+        pyr_nms_ms = float(stage[0] + stage[1] + stage[2]) / args.steps          # upload/convert + pyramid + NMS/localise
+        survey_achieved = survey_bytes * batch / (pyr_nms_ms / 1e3) / 1e9 if pyr_nms_ms > 0 else 0.0
         out = {
             "metric": "Mpixels/sec end-to-end (detect+affine+SIFT)", "value": value, "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -392,22 +403,28 @@ def main():
                          "algorithmic_bytes_per_image": blur_bytes, "survey_bytes_per_image_incl_nms": survey_bytes,
                          "traffic": ncu_traffic()[0],
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE octave-0 k_blur_tma<11> launch over "
-                                         "32 x 1920x1080 (ncu --set full, profiles/r1d_k_blur_tma_ncu.txt); algorithmic bytes of "
-                                         "that launch: %.0f" % (ncu_traffic()[1] or 0)},
+                                         "32 x 1920x1080 (ncu --set full, %s); algorithmic bytes of that launch: %.0f" % (
+                                             NCU_TRAFFIC_FILE, ncu_traffic()[1] or 0),
+                         # the same stage under SURVEY.md 8(d)'s wider definition: B_pyr (u8 ingest + every plane written once
+                         # and read once per consumer, NMS reads included) over the pyramid + NMS/localisation stage times
+                         "survey_b_pyr": {"bytes_per_image": survey_bytes, "stage_ms": pyr_nms_ms,
+                                          "achieved": survey_achieved, "frac": survey_achieved / peak if peak else None}},
             "clocks": clk,
             "host_cores": host_cores, "host_threads": host_threads,
         }
         if not args.no_cpu_baseline:
-            n_cpu = args.cpu_images or min(3 * host_cores, 192, batch)   # ~10-20 s of host work
+            per_proc = 16 if W * H <= 1920 * 1080 else (2 if W * H <= 3840 * 2160 else 1)      # >= 16 per process
+            n_cpu = min(args.cpu_images or per_proc * host_cores, batch)
             sample = images[:n_cpu].cpu().numpy()
             r = cpu_reference_run(sample, over, host_cores)
             cpu_v = r["mpix"] / r["wall_s"]
-            gpu_det = det.n_detected[:n_cpu].tolist() if world == 1 else None
+            gpu_det = det.n_detected[:n_cpu].tolist()        # rank 0's own images (the last call ran on the same batch)
             out["cpu_baseline"] = {
                 "value": cpu_v, "unit": "Mpix/s", "cores": r["workers"], "kind": r["kind"],
-                "sample": "first %d images of rank 0's batch, one per worker process, wall %.1f s" % (n_cpu, r["wall_s"]),
+                "sample": "first %d images of rank 0's batch over %d worker processes (%.1f per process), wall %.1f s" % (
+                    n_cpu, r["workers"], n_cpu / r["workers"], r["wall_s"]),
                 "single_core_mpix_s": H * W / 1e6 / r["single_core_s_per_image"],
-                "counts_match_gpu": (gpu_det == r["detections"]) if gpu_det is not None else None,
+                "counts_match_gpu": gpu_det == r["detections"],
             }
         print(json.dumps(out))
     det.close()
