@@ -650,3 +650,73 @@ def test_two_ranks_equal_one_gpu_and_gather_over_nccl(hb, tmp_path):
         assert [c[1] for c in x["counts"]] == det.n_described.tolist() and [c[0] for c in x["counts"]] == det.n_detected.tolist()
     assert sum(x["n_local"] for x in res) == det.total()
     det.close()
+
+
+SANITIZER_WORKER = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import hesaff_b200 as hb
+from tools.gen_textured import textured
+img = textured(640, 480, 1)                       # BASELINE configs[0]
+det = hb.AffineHessianDetector(hb.HessianAffineParams(), 0, 640, 480, max_batch=1)
+det.detectPyramidKeypoints(img)
+print("RESULT", int(det.n_detected[0]), int(det.n_described[0]), flush=True)
+det.close()
+'''
+
+
+@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
+def test_compute_sanitizer_on_config0(hb, tmp_path, tool):
+    """Hygiene (SURVEY 5, App. C), opt-in: HESAFF_SANITIZER=1 runs BASELINE configs[0] under compute-sanitizer.  memcheck:
+    no out-of-bounds / misaligned access in any kernel; racecheck: no shared-memory hazard (the describe kernels alias
+    their buffers between phases).  Minutes per tool, hence not in the default run."""
+    import shutil
+    import subprocess
+    import sys
+    if os.environ.get("HESAFF_SANITIZER") != "1":
+        pytest.skip("set HESAFF_SANITIZER=1 to run compute-sanitizer (slow)")
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(SANITIZER_WORKER)
+    r = subprocess.run([exe, "--tool", tool, "--error-exitcode", "77", sys.executable, str(script), root],
+                       capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+    assert "RESULT 5596 4976" in r.stdout                      # SURVEY 8(c) checksum of this fixture
+    out = r.stdout + r.stderr
+    assert ("ERROR SUMMARY: 0 errors" in out) if tool == "memcheck" else ("RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings)" in out), out[-2000:]
+
+
+def test_host_cli_on_two_gpus(hb, tmp_path):
+    """The C++ host with --gpus 2: contiguous blocks of files per GPU, one NCCL all-gather of the per-image counts; every
+    output file equals the single-GPU tool's."""
+    import subprocess
+    import torch
+    from tools.gen_textured import write_pgm
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "hesaff_b200", "host", "hesaff")
+    if not os.path.exists(exe):
+        pytest.skip("host CLI not built")
+    files = []
+    for s in range(3):
+        f = str(tmp_path / ("img%d.pgm" % s))
+        write_pgm(f, textured(320 + 16 * s, 240, 50 + s))      # different sizes: one context per file
+        files.append(f)
+    one = subprocess.run([exe] + files, capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stderr
+    want = [open(f + ".hesaff.sift").read() for f in files]
+    for f in files:
+        os.remove(f + ".hesaff.sift")
+    two = subprocess.run([exe, "--gpus", "2"] + files, capture_output=True, text=True, timeout=300)
+    assert two.returncode == 0, two.stderr
+    assert [open(f + ".hesaff.sift").read() for f in files] == want
+    l1, l2 = one.stdout.strip().splitlines(), two.stdout.strip().splitlines()
+    assert len(l2) == len(l1) + 1 and "counts all-gathered with NCCL" in l2[-1]
+    assert [ln.split(" in ")[0] for ln in l2[:-1]] == [ln.split(" in ")[0] for ln in l1]
+    tot = sum(int(ln.split()[1]) for ln in l1)
+    assert int(l2[-1].split(": ")[1].split()[0]) == tot
