@@ -715,7 +715,8 @@ def test_host_cli_on_two_gpus(hb, tmp_path):
     two = subprocess.run([exe, "--gpus", "2"] + files, capture_output=True, text=True, timeout=300)
     assert two.returncode == 0, two.stderr
     assert [open(f + ".hesaff.sift").read() for f in files] == want
-    l1, l2 = one.stdout.strip().splitlines(), two.stdout.strip().splitlines()
+    l1 = one.stdout.strip().splitlines()
+    l2 = [ln for ln in two.stdout.strip().splitlines() if not ln.startswith("NCCL version")]     # NCCL_DEBUG=VERSION banner
     assert len(l2) == len(l1) + 1 and "counts all-gathered with NCCL" in l2[-1]
     assert [ln.split(" in ")[0] for ln in l2[:-1]] == [ln.split(" in ")[0] for ln in l1]
     tot = sum(int(ln.split()[1]) for ln in l1)
