@@ -534,7 +534,7 @@ extern "C" int hesaff_create(hesaff_ctx **out, const hesaff_params *p, int devic
    c->mask_words_cap = g.mask_stride * chunk;
    c->scan_tmp_elems = std::max(ha_scan_tmp_elems(c->mask_words_cap), ha_scan_tmp_elems(c->cand_cap)) + 8;
    c->map_elems_cap = g.map_stride * chunk;
-   c->large_ctas = 148 * 3;
+   c->large_ctas = 148 * 4;
    c->scratch_per_cta = align_up(ha_describe_scratch_floats(c->maxP), 64);
    for (int l = 0; l < c->n_lanes; l++)
       if ((rc = alloc_lane(c, c->lane[l], g))) return rc;

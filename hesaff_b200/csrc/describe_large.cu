@@ -22,6 +22,9 @@
 #include "describe.cuh"
 
 #define LG_NT 256
+#ifndef LG_MINB
+#define LG_MINB 3
+#endif
 #define LG_B (82 * 82)
 #define LG_TS 84             // row stride of the row-filtered scratch plane T (floats; rows 16-byte aligned)
 
@@ -49,7 +52,7 @@ __device__ __forceinline__ float lg_sample(const void *__restrict__ im, int spit
 }
 
 template <bool U8>
-__global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__restrict__ arena, const Geom *__restrict__ g, Tables tb,
+__global__ void __launch_bounds__(LG_NT, LG_MINB) k_describe_large(const float *__restrict__ arena, const Geom *__restrict__ g, Tables tb,
                                                             Cand cand, const int *__restrict__ list, const int *__restrict__ list_n,
                                                             int *work_counter, float *scratch, size_t scratch_per_cta,
                                                             float *patch_dump, int dump_normalized,
@@ -123,40 +126,106 @@ __global__ void __launch_bounds__(LG_NT, 3) k_describe_large(const float *__rest
       const int lgLR = min(4, 31 - __clz(G2fit)), LR = 1 << lgLR, LJ = 32 >> lgLR;   // LR <= 16: two lanes share a 16-byte store
       const int G2 = LR;
       float2 *rb2 = reinterpret_cast<float2 *>(rowbuf);
-      const float invP = 1.0f / (float)P;
+      // source box of the sampling: the part of B behind the column table (B is idle until the column pass)
+      unsigned char *box = reinterpret_cast<unsigned char *>(B + ((4 * P + 3) & ~3));
+      const int box_cap = use_ctab ? (LG_B - ((4 * P + 3) & ~3)) * 4 : 0;
       __syncthreads();
       for (int r0 = 0; r0 < P; r0 += 2 * G2) {
          const int nrp = min(G2, (P - r0 + 1) >> 1);
          const int nrb = (nrp + LR - 1) >> lgLR, njb = (HA_PATCH + LJ - 1) / LJ;
-         // ---- sampling: item = (row pair, column) ---------------------------------------------------------------------
-         for (int t = tid; t < nrp * P; t += NT) {
-            const int rp = ha_fast_div(t, invP), xx = t - rp * P;
-            const int ja = r0 + 2 * rp, jb = min(ja + 1, P - 1);
-            float4 c;
-            float rxa = 0.f, rxb = 0.f;
-            if (use_ctab) c = ctab[xx];
-            else {
-               // general A (never produced by k_affine; kept for completeness): per-sample column terms
-               const int ii = xx - half;
-               rxa = x + (float)(ja - half) * a12; rxb = x + (float)(jb - half) * a12;
-               const float wx = rxa + (float)ii * a11, fl = floorf(wx), fx = wx - fl;
-               c = make_float4(__int_as_float((int)fl), fx, 1.0f - fx, (float)ii * a21);
+         // ---- sampling: item = (row pair, column).  u8 source: the band is cut into column chunks whose source bounding
+         // box fits the idle part of B; the box is copied with coalesced 16-byte loads and the samples come from shared
+         // memory (the direct form gathers four bytes per sample from up to 32 different cache lines per warp load: 78 % of
+         // the kernel's L1 requests and its largest stall) -----------------------------------------------------------------
+         const int jlo = r0, jhi = min(r0 + 2 * nrp - 1, P - 1);
+         int CW = P;                                       // columns per chunk
+         if (U8 && use_ctab) {
+            for (;;) {
+               // widest / tallest box of a chunk of CW columns (positions are monotone in i and j)
+               const float wxspan = (float)(CW - 1) * a11;
+               const int bwmax = (((int)wxspan + 3 + 15 + 15) & ~15);
+               const float hy = (float)(jhi - jlo) * a22 + (float)(CW - 1) * fabsf(a21);
+               const int brmax = (int)hy + 4;
+               if (bwmax * brmax <= box_cap || CW <= 32) break;
+               CW = (CW + 1) >> 1;
             }
-            float wya = (y + (float)(ja - half) * a22) + c.w, wyb = (y + (float)(jb - half) * a22) + c.w;
-            const float fya = floorf(wya), fyb = floorf(wyb);
-            wya -= fya; wyb -= fyb;
-            float va, vb;
-            if (use_ctab || rxa == rxb) {
-               const int xi = __float_as_int(c.x);
-               va = lg_sample<U8>(im, spitch, (int)fya * spitch + xi, c.y, c.z, wya);
-               vb = lg_sample<U8>(im, spitch, (int)fyb * spitch + xi, c.y, c.z, wyb);
+         }
+         for (int c0 = 0; c0 < P; c0 += CW) {
+            const int c1 = min(c0 + CW, P) - 1;
+            bool staged = false;
+            int bx0 = 0, by0 = 0, bw = 0;
+            if (U8 && use_ctab) {
+               const float xl = x + (float)(c0 - half) * a11, xr = x + (float)(c1 - half) * a11;
+               const float ya = y + (float)(jlo - half) * a22, yb = y + (float)(jhi - half) * a22;
+               const float sl = (float)(c0 - half) * a21, sr = (float)(c1 - half) * a21;
+               const float y00 = ya + sl, y01 = ya + sr, y10 = yb + sl, y11 = yb + sr;
+               const int xmin = (int)floorf(fminf(xl, xr)), xmax = (int)floorf(fmaxf(xl, xr)) + 1;
+               by0 = (int)floorf(fminf(fminf(y00, y01), fminf(y10, y11)));
+               const int ymax = (int)floorf(fmaxf(fmaxf(y00, y01), fmaxf(y10, y11))) + 1;
+               bx0 = xmin & ~15;
+               bw = ((xmax - bx0 + 1) + 15) & ~15;
+               const int brows = ymax - by0 + 1;
+               staged = bw * brows <= box_cap;
+               if (staged) {
+                  const int wq = bw >> 4;
+                  const float invwq = 1.0f / (float)wq;
+                  const unsigned char *src = reinterpret_cast<const unsigned char *>(im) + (size_t)by0 * spitch + bx0;
+                  for (int t = tid; t < brows * wq; t += NT) {
+                     const int r = ha_fast_div(t, invwq), q = t - r * wq;
+                     *reinterpret_cast<uint4 *>(box + r * bw + 16 * q) = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * spitch + 16 * q));
+                  }
+               }
+               __syncthreads();
+            }
+            const int ncol = c1 - c0 + 1;
+            const float invC = 1.0f / (float)ncol;
+            if (staged) {
+               const int off0 = -(by0 * bw + bx0);
+               for (int t = tid; t < nrp * ncol; t += NT) {
+                  const int rp = ha_fast_div(t, invC), xx = c0 + (t - rp * ncol);
+                  const int ja = r0 + 2 * rp, jb = min(ja + 1, P - 1);
+                  const float4 c = ctab[xx];
+                  float wya = (y + (float)(ja - half) * a22) + c.w, wyb = (y + (float)(jb - half) * a22) + c.w;
+                  const float fya = floorf(wya), fyb = floorf(wyb);
+                  wya -= fya; wyb -= fyb;
+                  const int xi = __float_as_int(c.x);
+                  const unsigned char *pa = box + (off0 + (int)fya * bw + xi), *pb = box + (off0 + (int)fyb * bw + xi);
+                  const float va = (1.0f - wya) * (c.z * (float)pa[0] + c.y * (float)pa[1]) + (wya) * (c.z * (float)pa[bw] + c.y * (float)pa[bw + 1]);
+                  const float vb = (1.0f - wyb) * (c.z * (float)pb[0] + c.y * (float)pb[1]) + (wyb) * (c.z * (float)pb[bw] + c.y * (float)pb[bw + 1]);
+                  rb2[rp * RS2 + R + xx] = make_float2(va, vb);
+               }
             } else {
-               const int ii = xx - half;
-               const float wxb = rxb + (float)ii * a11, flb = floorf(wxb), fxb = wxb - flb;
-               va = lg_sample<U8>(im, spitch, (int)fya * spitch + __float_as_int(c.x), c.y, c.z, wya);
-               vb = lg_sample<U8>(im, spitch, (int)fyb * spitch + (int)flb, fxb, 1.0f - fxb, wyb);
+               for (int t = tid; t < nrp * ncol; t += NT) {
+                  const int rp = ha_fast_div(t, invC), xx = c0 + (t - rp * ncol);
+                  const int ja = r0 + 2 * rp, jb = min(ja + 1, P - 1);
+                  float4 c;
+                  float rxa = 0.f, rxb = 0.f;
+                  if (use_ctab) c = ctab[xx];
+                  else {
+                     // general A (never produced by k_affine; kept for completeness): per-sample column terms
+                     const int ii = xx - half;
+                     rxa = x + (float)(ja - half) * a12; rxb = x + (float)(jb - half) * a12;
+                     const float wx = rxa + (float)ii * a11, fl = floorf(wx), fx = wx - fl;
+                     c = make_float4(__int_as_float((int)fl), fx, 1.0f - fx, (float)ii * a21);
+                  }
+                  float wya = (y + (float)(ja - half) * a22) + c.w, wyb = (y + (float)(jb - half) * a22) + c.w;
+                  const float fya = floorf(wya), fyb = floorf(wyb);
+                  wya -= fya; wyb -= fyb;
+                  float va, vb;
+                  if (use_ctab || rxa == rxb) {
+                     const int xi = __float_as_int(c.x);
+                     va = lg_sample<U8>(im, spitch, (int)fya * spitch + xi, c.y, c.z, wya);
+                     vb = lg_sample<U8>(im, spitch, (int)fyb * spitch + xi, c.y, c.z, wyb);
+                  } else {
+                     const int ii = xx - half;
+                     const float wxb = rxb + (float)ii * a11, flb = floorf(wxb), fxb = wxb - flb;
+                     va = lg_sample<U8>(im, spitch, (int)fya * spitch + __float_as_int(c.x), c.y, c.z, wya);
+                     vb = lg_sample<U8>(im, spitch, (int)fyb * spitch + (int)flb, fxb, 1.0f - fxb, wyb);
+                  }
+                  rb2[rp * RS2 + R + xx] = make_float2(va, vb);
+               }
             }
-            rb2[rp * RS2 + R + xx] = make_float2(va, vb);
+            if (c1 + 1 < P) __syncthreads();     // the next chunk's box overwrites this one
          }
          __syncthreads();
          for (int t = tid; t < nrp * (2 * R + 1); t += NT) {   // replicate R columns left, R + 1 right (BORDER_REPLICATE)
@@ -276,7 +345,7 @@ static int large_smem_bytes(int maxP)
                 sizeof(float) * (LG_B + 4 + (size_t)large_rowbuf_floats(maxP)));
 }
 
-int ha_describe_large_max_ctas_per_sm(int maxP) { return std::max(1, std::min(3, 227 * 1024 / (large_smem_bytes(maxP) + 1024))); }
+int ha_describe_large_max_ctas_per_sm(int maxP) { return std::max(1, std::min(LG_MINB, 227 * 1024 / (large_smem_bytes(maxP) + 1024))); }
 
 void ha_launch_describe_large(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,
                               float *scratch, size_t scratch_per_cta, int ctas_per_sm, int maxP, int src_u8, float *patch_dump,
