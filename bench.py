@@ -130,11 +130,37 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------
 # CPU side: the reference's own code on host cores (test/measurement infrastructure, never the product path)
 # --------------------------------------------------------------------------------------------------------
+_CV2_CB = None
+
+
+def _install_cv2_blur(orc):
+    """--cpu-blur cv2: the reference build calls the real OpenCV's GaussianBlur (single-threaded) instead of the stand-in's
+    (oracle/shim/cv_shim.cpp: orc_shim_set_blur).  BASELINE.md 3.1; the ctypes round trip adds a few microseconds per call."""
+    global _CV2_CB
+    if _CV2_CB is not None:
+        return
+    import ctypes as C
+    import cv2
+    import numpy as np
+    cv2.setNumThreads(1)
+    FP = C.POINTER(C.c_float)
+
+    def blur(src, dst, rows, cols, sstep, dstep, ksize, sigma):
+        a = np.ctypeslib.as_array(src, shape=(rows, sstep // 4))[:, :cols]
+        d = np.ctypeslib.as_array(dst, shape=(rows, dstep // 4))[:, :cols]
+        cv2.GaussianBlur(a, (ksize, ksize), sigma, dst=d, sigmaY=sigma, borderType=cv2.BORDER_REPLICATE)
+
+    _CV2_CB = C.CFUNCTYPE(None, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double)(blur)
+    orc.lib.orc_shim_set_blur(_CV2_CB)
+
+
 def _cpu_worker(args):
     kind, img_bytes, h, w, over = args
     import numpy as np
     from oracle import oracle
     orc = oracle.load(kind)
+    if os.environ.get("HESAFF_CPU_BLUR") == "cv2" and kind == "ref":
+        _install_cv2_blur(orc)
     img = np.frombuffer(img_bytes, np.uint8).reshape(h, w).astype(np.float32)
     t = time.perf_counter()
     d = orc.detect(img, orc.default_params(**over))
@@ -213,6 +239,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override images per GPU")
     ap.add_argument("--cpu-images", type=int, default=0, help="CPU sample size (default: 16 images per worker process for the cpu_baseline leg, BASELINE.md 3.3; 8 per timed step of --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-blur", default="shim", choices=["shim", "cv2"],
+                    help="--impl reference only: blur of the CPU build = the stand-in pinned bit-identical to OpenCV (default) or the real cv2")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +265,9 @@ def main():
         # the reference's own CPU implementation on this box's host cores; rank 0 only
         if rank != 0:
             return 0
+        if args.cpu_blur == "cv2":
+            os.environ["HESAFF_CPU_BLUR"] = "cv2"
+            config["cpu_blur"] = "cv2.GaussianBlur (OpenCV %s, 1 thread) through a ctypes callback" % __import__("cv2").__version__
         import torch
         from tools.gen_textured import textured
         # every timed step: 8 images per worker process (about 30 s of host work at 1080p); warm-up steps: one per process

@@ -11,6 +11,7 @@
 #include <fstream>
 #include <sstream>
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg)
@@ -592,6 +593,15 @@ static int flush_lane_output(hesaff_ctx *c, Lane &L)
 
 enum InFmt { IN_U8 = 0, IN_F32 = 1, IN_RGB8 = 2 };
 
+// NVTX ranges mark the host-side enqueue of every stage of a chunk (nsys / ncu --nvtx correlate them with the kernels);
+// the guard keeps the range stack balanced on the error returns
+struct NvtxStages {
+   int depth = 0;
+   explicit NvtxStages(const char *outer) { nvtxRangePushA(outer); depth = 1; }
+   void next(const char *name) { if (depth > 1) nvtxRangePop(); else depth = 2; nvtxRangePushA(name); }
+   ~NvtxStages() { while (depth-- > 0) nvtxRangePop(); }
+};
+
 // `ptrs` (optional, host input only): image i starts at ptrs[i] instead of images + i * img_stride
 static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int W, int H, size_t row_pitch,
                        size_t img_stride, int on_device, void *stream_, const void *const *ptrs = nullptr)
@@ -668,6 +678,8 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       { int rc = flush_lane_output(c, L); if (rc) return rc; }
       c->last_chunks++;
       if (c->profiling) cudaEventRecord(L.ev[0], st);
+      NvtxStages nvtx("hesaff:chunk");
+      nvtx.next("hesaff:upload+convert");
       // ---- stage 0: upload + gray float image (hesaff.cpp:138-148) ---------------------------------
       const char *src = ptrs ? nullptr : (const char *)images + (size_t)start * img_stride;
       const void *dsrc = src;
@@ -701,6 +713,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       else if (fmt == IN_RGB8) ha_launch_convert_rgb8((const uint8_t *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       else ha_launch_convert_f32((const float *)dsrc, d_row_pitch, d_img_stride, img_plane, g, cn, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[1], st);
+      nvtx.next("hesaff:pyramid");
 
       // ---- stage 1: pyramid (pyramid.cpp:261-292, 224-259) ------------------------------------------
       size_t bev = 0;
@@ -739,6 +752,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
          }
       }
       if (c->profiling) cudaEventRecord(L.ev[2], st);
+      nvtx.next("hesaff:nms+localize");
 
       // ---- stage 2: extrema, ordered compaction, localisation, dedup ------------------------------------
       const size_t nwords = g.mask_stride * cn;
@@ -749,6 +763,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       CK(cudaMemsetAsync(L.map, 0xFF, sizeof(uint32_t) * g.map_stride * cn, st));
       ha_launch_localize(L.arena, c->d_geom, L.cand, d_count, c->cand_cap, L.map, st, c->lc);
       if (c->profiling) cudaEventRecord(L.ev[3], st);
+      nvtx.next("hesaff:affine-shape");
 
       // ---- stage 3: affine shape ---------------------------------------------------------------------
       CK(cudaMemsetAsync(L.counters, 0, sizeof(int) * 7, st));
@@ -762,11 +777,13 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
          if (prev_done) CK(cudaStreamWaitEvent(st, prev_done, 0));
       }
 
+      nvtx.next("hesaff:patch+sift");
       // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
       ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
                          c->large_ctas, c->maxP, fmt == IN_U8, nullptr, 0, nullptr, st, c->lc, L.aux, L.ev_fork, L.ev_join);
       if (c->profiling) cudaEventRecord(L.ev[5], st);
 
+      nvtx.next("hesaff:compact");
       // ---- stage 5: ordered compaction into Keypoint records -------------------------------------------
       ha_launch_scan_flags(L.cand.flags, HA_F_DESC, d_count, c->cand_cap, L.desc_off, L.scan_tmp, st, c->lc);
       // records of this chunk start at the running total of the previous chunks (device-side base); chunk order is
@@ -780,6 +797,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
       CK(cudaEventRecord(L.done, st));
       prev_done = L.done;
       L.pending_chunk = k;
+
       if (c->profiling) {
          cudaEventRecord(L.ev[6], st);
          CK(cudaEventSynchronize(L.ev[6]));
