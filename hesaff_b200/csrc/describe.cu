@@ -206,7 +206,7 @@ template <int BIN, int NT, bool U8>
 __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__restrict__ arena, const Geom *__restrict__ g, Tables tb,
                                                  Cand cand, const int *__restrict__ list, const int *__restrict__ list_n,
                                                  int *work_counter, float *patch_dump, int dump_normalized,
-                                                 const uint32_t *__restrict__ dump_index)
+                                                 const uint32_t *__restrict__ dump_index, int no_stage)
 {
    typedef DescPlan<BIN> PL;
    extern __shared__ __align__(16) unsigned char dsm[];
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
                bx0 = xmin & ~15;
                bw = ((xmax - bx0 + 1) + 15) & ~15;
                brows = ymax - by0 + 1;
-               staged = bw * brows <= PL::SB * 4;
+               staged = bw * brows <= PL::SB * 4 && !no_stage;
             }
             for (int t = tid; t < P; t += NT) {
                const int ii = t - half;
@@ -479,6 +479,14 @@ int ha_describe_smem_bytes(int bin)
    return 0;
 }
 
+// HESAFF_NO_STAGE=1 (tests): sample the u8 source directly instead of from the shared-memory box -- the fallback every
+// kernel takes when a footprint's bounding box does not fit; records must not change
+int ha_no_stage()
+{
+   static const int v = getenv("HESAFF_NO_STAGE") && atoi(getenv("HESAFF_NO_STAGE")) > 0;
+   return v;
+}
+
 struct DescLaunch {
    const float *arena; const Geom *dg; Tables tb; Cand cand; Bins bins; int *work;
    float *patch_dump; int dump_normalized; const uint32_t *dump_index; int src_u8;
@@ -491,11 +499,11 @@ static void launch_desc(const DescLaunch &a, int ctas_per_sm, cudaStream_t st)
    if (a.src_u8) {
       cudaFuncSetAttribute(k_describe<BIN, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       k_describe<BIN, NT, true><<<148 * ctas_per_sm, NT, smem, st>>>(a.arena, a.dg, a.tb, a.cand, a.bins.list[BIN], a.bins.count + BIN,
-                                                                     a.work + BIN, a.patch_dump, a.dump_normalized, a.dump_index);
+                                                                     a.work + BIN, a.patch_dump, a.dump_normalized, a.dump_index, ha_no_stage());
    } else {
       cudaFuncSetAttribute(k_describe<BIN, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       k_describe<BIN, NT, false><<<148 * ctas_per_sm, NT, smem, st>>>(a.arena, a.dg, a.tb, a.cand, a.bins.list[BIN], a.bins.count + BIN,
-                                                                      a.work + BIN, a.patch_dump, a.dump_normalized, a.dump_index);
+                                                                      a.work + BIN, a.patch_dump, a.dump_normalized, a.dump_index, ha_no_stage());
    }
 }
 

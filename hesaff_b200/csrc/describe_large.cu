@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(LG_NT, LG_MINB) k_describe_large(const float *
                                                             Cand cand, const int *__restrict__ list, const int *__restrict__ list_n,
                                                             int *work_counter, float *scratch, size_t scratch_per_cta,
                                                             float *patch_dump, int dump_normalized,
-                                                            const uint32_t *__restrict__ dump_index, int rowbuf_floats)
+                                                            const uint32_t *__restrict__ dump_index, int rowbuf_floats, int no_stage)
 {
    constexpr int NT = LG_NT;
    extern __shared__ __align__(16) unsigned char dsm[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(LG_NT, LG_MINB) k_describe_large(const float *
       float2 *rb2 = reinterpret_cast<float2 *>(rowbuf);
       // source box of the sampling: the part of B behind the column table (B is idle until the column pass)
       unsigned char *box = reinterpret_cast<unsigned char *>(B + ((4 * P + 3) & ~3));
-      const int box_cap = use_ctab ? (LG_B - ((4 * P + 3) & ~3)) * 4 : 0;
+      const int box_cap = (use_ctab && !no_stage) ? (LG_B - ((4 * P + 3) & ~3)) * 4 : 0;
       __syncthreads();
       for (int r0 = 0; r0 < P; r0 += 2 * G2) {
          const int nrp = min(G2, (P - r0 + 1) >> 1);
@@ -356,11 +356,11 @@ void ha_launch_describe_large(const float *arena, const Geom *dg, Tables tb, Can
       cudaFuncSetAttribute(k_describe_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // grows with maxP
       k_describe_large<true><<<148 * ctas_per_sm, LG_NT, smem, st>>>(arena, dg, tb, cand, bins.list[2], bins.count + 2, work_counters + 2, scratch,
                                                                    scratch_per_cta, patch_dump, dump_normalized, dump_index,
-                                                                   large_rowbuf_floats(maxP));
+                                                                   large_rowbuf_floats(maxP), ha_no_stage());
    } else {
       cudaFuncSetAttribute(k_describe_large<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       k_describe_large<false><<<148 * ctas_per_sm, LG_NT, smem, st>>>(arena, dg, tb, cand, bins.list[2], bins.count + 2, work_counters + 2, scratch,
                                                                     scratch_per_cta, patch_dump, dump_normalized, dump_index,
-                                                                    large_rowbuf_floats(maxP));
+                                                                    large_rowbuf_floats(maxP), ha_no_stage());
    }
 }

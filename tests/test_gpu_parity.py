@@ -166,6 +166,10 @@ def test_large_patches(hb, port_oracle):
         A = [k["a11"][i], k["a12"][i], k["a21"][i], k["a22"][i]]
         rej, patch = port_oracle.normalize_affine(f, float(k["x"][i]), float(k["y"][i]), float(k["s"][i]), A)
         assert not rej and np.array_equal(P[i], patch), (i, float(k["s"][i]), np.abs(P[i] - patch).max())
+    # the float-source kernels (fp32 / colour input) sample the float image instead of the u8 copy: same records
+    detf = run(hb, f)
+    assert detf.keys().tobytes() == k.tobytes()
+    detf.close()
     det.close()
 
 
@@ -467,7 +471,7 @@ def test_schedule_knobs_do_not_change_results(hb, tmp_path):
     script.write_text(KNOB_WORKER)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for env in ({}, {"HESAFF_OVERLAP": "0"}, {"HESAFF_PLAN": "T2,S2,D1,E1,M1,L1"}, {"HESAFF_PLAN": "S3;L2"},
+    for env in ({}, {"HESAFF_OVERLAP": "0"}, {"HESAFF_PLAN": "T2,S2,D1,E1,M1,L1"}, {"HESAFF_PLAN": "S3;L2"}, {"HESAFF_NO_STAGE": "1"},
                 {"HESAFF_PLAN": "L1,M2,E3,D4,S7,T9;T1", "HESAFF_CHUNK": "1"}):
         e = dict(os.environ)
         e.update(env)
