@@ -444,7 +444,9 @@ def main():
             "host_cores": host_cores, "host_threads": host_threads,
         }
         if not args.no_cpu_baseline:
-            per_proc = 16 if W * H <= 1920 * 1080 else (2 if W * H <= 3840 * 2160 else 1)      # >= 16 per process
+            # >= 16 images per process at N=1 (about a minute of host work); at N>1 the baseline is only
+            # the per-rank counts check (one image per process), the CPU figure belongs to the N=1 line
+            per_proc = (16 if W * H <= 1920 * 1080 else (2 if W * H <= 3840 * 2160 else 1)) if world == 1 else 1
             n_cpu = min(args.cpu_images or per_proc * host_cores, batch)
             sample = images[:n_cpu].cpu().numpy()
             r = cpu_reference_run(sample, over, host_cores)
