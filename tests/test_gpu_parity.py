@@ -670,6 +670,48 @@ det.close()
 '''
 
 
+SANITIZER_WORKER_LARGE = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import cv2
+import hesaff_b200 as hb
+rng = np.random.default_rng(5)
+g = cv2.GaussianBlur(rng.standard_normal((600, 800)).astype(np.float32), (0, 0), 9.0)
+img = np.clip(128 + 60 * g / g.std(), 0, 255).astype(np.uint8)      # smooth: hundreds of source patches beyond 95 px
+det = hb.AffineHessianDetector(hb.HessianAffineParams(), 0, 800, 600, max_batch=2)
+for batch in (np.stack([img, img[::-1].copy()]), np.stack([img, img[::-1].copy()]).astype(np.float32)):   # u8- and float-source kernels
+    det.detectPyramidKeypoints(batch)
+    k = det.keys()
+    P = 2 * np.ceil(k["s"] * det.par.desc_factor).astype(int) + 3
+    print("LARGE", int((P > 95).sum()), flush=True)
+det.close()
+'''
+
+
+@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
+def test_compute_sanitizer_on_large_patches(hb, tmp_path, tool):
+    """The LARGE-bin kernel (shared-memory source boxes, lane-exchanged scratch stores) under compute-sanitizer; opt-in."""
+    import shutil
+    import subprocess
+    import sys
+    if os.environ.get("HESAFF_SANITIZER") != "1":
+        pytest.skip("set HESAFF_SANITIZER=1 to run compute-sanitizer (slow)")
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(SANITIZER_WORKER_LARGE)
+    r = subprocess.run([exe, "--tool", tool, "--error-exitcode", "77", sys.executable, str(script), root],
+                       capture_output=True, text=True, timeout=3000)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    n = [int(ln.split()[1]) for ln in r.stdout.splitlines() if ln.startswith("LARGE")]
+    assert len(n) == 2 and n[0] == n[1] > 300
+    assert ("ERROR SUMMARY: 0 errors" in out) if tool == "memcheck" else ("RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings)" in out), out[-2000:]
+
+
 @pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
 def test_compute_sanitizer_on_config0(hb, tmp_path, tool):
     """Hygiene (SURVEY 5, App. C), opt-in: HESAFF_SANITIZER=1 runs BASELINE configs[0] under compute-sanitizer.  memcheck:
