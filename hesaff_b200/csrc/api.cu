@@ -779,7 +779,7 @@ static int detect_impl(hesaff_ctx *c, const void *images, InFmt fmt, int n, int 
 
       nvtx.next("hesaff:patch+sift");
       // ---- stage 4: patch normalisation + SIFT ----------------------------------------------------------
-      ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
+      ha_launch_describe(L.arena, c->d_geom, c->geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
                          c->large_ctas, c->maxP, fmt == IN_U8, nullptr, 0, nullptr, st, c->lc, L.aux, L.ev_fork, L.ev_join);
       if (c->profiling) cudaEventRecord(L.ev[5], st);
 
@@ -1033,7 +1033,7 @@ extern "C" int hesaff_debug_patches(hesaff_ctx *c, int normalized, float *out, s
    if ((rc = dmalloc(&d, (size_t)c->total_desc * HA_PATCH_PX))) return rc;
    Lane &L = c->lane[0];
    CK(cudaMemsetAsync(L.counters + 1, 0, sizeof(int) * 6, L.stream));
-   ha_launch_describe(L.arena, c->d_geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
+   ha_launch_describe(L.arena, c->d_geom, c->geom, c->tables, L.cand, L.bins, L.counters + 1, L.scratch, c->scratch_per_cta,
                       c->large_ctas, c->maxP, c->last_u8, d, normalized, L.desc_off, L.stream, c->lc);
    CK(cudaStreamSynchronize(L.stream));
    cudaError_t e = cudaMemcpy(out, d, sizeof(float) * HA_PATCH_PX * c->total_desc, cudaMemcpyDeviceToHost);

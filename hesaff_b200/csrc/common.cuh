@@ -177,7 +177,7 @@ void ha_launch_localize(const float *arena, const Geom *dg, Cand cand, const uin
                         uint32_t *map, cudaStream_t st, LaunchCounter &lc);
 void ha_launch_affine(const float *arena, const Geom *dg, Tables tb, Cand cand, const uint32_t *count, uint32_t cap,
                       const uint32_t *map, int *n_det, Bins bins, int *work_counter, cudaStream_t st, LaunchCounter &lc);
-void ha_launch_describe(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,
+void ha_launch_describe(const float *arena, const Geom *dg, const Geom &hg, Tables tb, Cand cand, Bins bins, int *work_counters,
                         float *scratch, size_t scratch_per_cta, int large_ctas, int maxP, int src_u8, float *patch_dump,
                         int dump_normalized, const uint32_t *dump_index, cudaStream_t st, LaunchCounter &lc,
                         cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);

@@ -202,8 +202,16 @@ template <int NT> struct DescHead {
 #endif
 #define DESC_MINB(BIN) ((BIN) == 3 ? DESC_MINB_TINY : ((BIN) == 0 ? 7 : ((BIN) == 4 ? 4 : ((BIN) == 5 ? 3 : 2))))
 
+// what the kernel needs of the geometry, passed by value: kernel parameters live in the constant bank and are used as
+// instruction operands, so they cost no registers over the keypoint loop (read from the Geom in memory they cost eleven)
+struct DescGeom {
+   int cols, rows, pitch, pitch8;
+   float mrSize;
+   unsigned long long arena_stride, img_off, img8_off;
+};
+
 template <int BIN, int NT, bool U8>
-__global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__restrict__ arena, const Geom *__restrict__ g, Tables tb,
+__global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__restrict__ arena, const DescGeom g, Tables tb,
                                                  Cand cand, const int *__restrict__ list, const int *__restrict__ list_n,
                                                  int *work_counter, float *patch_dump, int dump_normalized,
                                                  const uint32_t *__restrict__ dump_index, int no_stage)
@@ -228,9 +236,9 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
 
    const int tid = threadIdx.x;
    const int nwork = *list_n;
-   const int cols = g->W, rows = g->H, pitch = g->pitch[0], pitch8 = g->pitch8;
-   const float mrSize = g->mrSize;
-   const unsigned long long arena_stride = g->arena_stride, img_off = g->img_off, img8_off = g->img8_off;
+   const int cols = g.cols, rows = g.rows, pitch = g.pitch, pitch8 = g.pitch8;
+   const float mrSize = g.mrSize;
+   const unsigned long long arena_stride = g.arena_stride, img_off = g.img_off, img8_off = g.img8_off;
 
    // prefetch pipeline state (thread 0): ticket of item k+2, list entry of item k+1 (HA_LIST_NONE: none)
    int pf_w = -1;
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
          }
       }
       float r_tap = 0.f;
+      bool committed = false;
       {
          const uint32_t en = k >= -1 ? sh.enext : HA_LIST_NONE;              // written at the end of iteration k-1
          if (en != HA_LIST_NONE && tid < 16) r_tap = __ldg(tb.pk16 + HA_LIST_M(en) * 16 + tid);
@@ -413,6 +422,17 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
 #endif
          }
          if (!rejected) {   // uniform across the CTA
+            // The prefetched item has arrived by now (the sampling and the blur ran since its loads were issued): park it
+            // in shared memory here, so that its registers are free during the SIFT stage.  Nobody reads the other
+            // parameter slot, the other tap row or sh.enext before the top of the next iteration.
+            if (tid == 0) {
+               sh.par[cur ^ 1] = r_it;
+               sh.enext = r_e;
+               pf_e = r_e;
+               pf_w = r_w;
+            }
+            if (tid < 16) sh.kern[cur ^ 1][tid] = r_tap;
+            committed = true;
 #if defined(HA_ABL) && HA_ABL == 1
             if (tid == 0) cand.flags[i] |= HA_F_DESC;
 #else
@@ -448,15 +468,16 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
 #endif
          }
       }
-      __syncthreads();         // every thread has read sh.enext / sh.par[cur] before they are overwritten below
-      // ---- commit the prefetched state for the next iterations -----------------------------------------------------
-      if (tid == 0) {
-         sh.par[cur ^ 1] = r_it;
-         sh.enext = r_e;
-         pf_e = r_e;
-         pf_w = r_w;
+      if (!committed) {         // prologue iterations and rejected keypoints (uniform)
+         __syncthreads();      // every thread has read sh.enext / sh.par[cur] before they are overwritten below
+         if (tid == 0) {
+            sh.par[cur ^ 1] = r_it;
+            sh.enext = r_e;
+            pf_e = r_e;
+            pf_w = r_w;
+         }
+         if (tid < 16) sh.kern[cur ^ 1][tid] = r_tap;
       }
-      if (tid < 16) sh.kern[cur ^ 1][tid] = r_tap;
    }
 }
 
@@ -488,7 +509,7 @@ int ha_no_stage()
 }
 
 struct DescLaunch {
-   const float *arena; const Geom *dg; Tables tb; Cand cand; Bins bins; int *work;
+   const float *arena; DescGeom dg; Tables tb; Cand cand; Bins bins; int *work;
    float *patch_dump; int dump_normalized; const uint32_t *dump_index; int src_u8;
 };
 
@@ -516,12 +537,13 @@ static const char *describe_plan()
    return e ? e : "T8,S5,D3,E2,M1;L3,M1";
 }
 
-void ha_launch_describe(const float *arena, const Geom *dg, Tables tb, Cand cand, Bins bins, int *work_counters,
+void ha_launch_describe(const float *arena, const Geom *dg, const Geom &hg, Tables tb, Cand cand, Bins bins, int *work_counters,
                         float *scratch, size_t scratch_per_cta, int large_ctas, int maxP, int src_u8, float *patch_dump,
                         int dump_normalized, const uint32_t *dump_index, cudaStream_t st, LaunchCounter &lc,
                         cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
-   const DescLaunch a{arena, dg, tb, cand, bins, work_counters, patch_dump, dump_normalized, dump_index, src_u8};
+   const DescGeom geo{hg.W, hg.H, hg.pitch[0], hg.pitch8, hg.mrSize, hg.arena_stride, hg.img_off, hg.img8_off};
+   const DescLaunch a{arena, geo, tb, cand, bins, work_counters, patch_dump, dump_normalized, dump_index, src_u8};
    const int per_sm = 227 * 1024;
    int large_slot = 0;                     // LARGE launches running side by side need their own scratch planes
    unsigned seen = 0;                      // bins the plan has launched
