@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(LG_NT, LG_MINB) k_describe_large(const float *
 }
 
 // One padded row pair = R + P + R + 2 float2, where R = taps/2 of the per-patch blur (sigma = 1.5*P0/41,
-// helpers.cpp:293).  The band buffer holds at least one row pair of the widest possible patch and 24 KB otherwise.
+// helpers.cpp:293).  The band buffer holds at least one row pair of the widest possible patch and 40 KB otherwise.
 static int large_row_stride(int maxP)
 {
    const float sigma = 1.5f * ((float)maxP / (float)HA_PATCH);
@@ -335,7 +335,12 @@ static int large_row_stride(int maxP)
    if (n % 2 == 0) n++;
    return (maxP + 2 * (n / 2) + 2) | 1;
 }
-static int large_rowbuf_floats(int maxP) { return std::max(6144, 2 * large_row_stride(maxP) + 8); }
+// 40 KB: 16 row pairs per band up to P ~ 260 (measured: 6144 floats +3.5 % on the stage, 12288 at 2 CTAs/SM +2.5 %; a layout
+// with the 82 x 82 grid aliased onto the band buffer and 50 KB of it also +2.5 %)
+#ifndef LG_ROWBUF
+#define LG_ROWBUF 10240
+#endif
+static int large_rowbuf_floats(int maxP) { return std::max(LG_ROWBUF, 2 * large_row_stride(maxP) + 8); }
 // rows of the row-filtered scratch plane T per CTA: R + P + R
 size_t ha_describe_scratch_floats(int maxP) { return (size_t)(large_row_stride(maxP) + 2) * LG_TS; }
 
