@@ -335,8 +335,9 @@ static int large_row_stride(int maxP)
    if (n % 2 == 0) n++;
    return (maxP + 2 * (n / 2) + 2) | 1;
 }
-// 40 KB: 16 row pairs per band up to P ~ 260 (measured: 6144 floats +3.5 % on the stage, 12288 at 2 CTAs/SM +2.5 %; a layout
-// with the 82 x 82 grid aliased onto the band buffer and 50 KB of it also +2.5 %)
+// 40 KB: 16 row pairs per band up to P ~ 260, and 76 KB per CTA = two CTAs per SM beside three TINY CTAs of the main stream
+// (measured on the describe stage: 24 KB / 39 KB at three CTAs per SM +4 % / +2.5 %, 48 KB +4 %, 56 KB +8 %, a 128-register
+// build +8 %, a layout with the 82 x 82 grid aliased onto a 50 KB band buffer +2.5 %)
 #ifndef LG_ROWBUF
 #define LG_ROWBUF 10240
 #endif
