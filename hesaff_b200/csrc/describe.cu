@@ -534,7 +534,7 @@ static void launch_desc(const DescLaunch &a, int ctas_per_sm, cudaStream_t st)
 static const char *describe_plan()
 {
    static const char *e = getenv("HESAFF_PLAN");
-   return e ? e : "T8,S5,D3,E2,M1;L3,M1";
+   return e ? e : "T8,S5,D3,E2,M1;L2,M1";
 }
 
 void ha_launch_describe(const float *arena, const Geom *dg, const Geom &hg, Tables tb, Cand cand, Bins bins, int *work_counters,
