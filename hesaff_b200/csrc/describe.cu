@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
          if (!rejected) {   // uniform across the CTA
             // The prefetched item has arrived by now (the sampling and the blur ran since its loads were issued): park it
             // in shared memory here, so that its registers are free during the SIFT stage.  Nobody reads the other
-            // parameter slot, the other tap row or sh.enext before the top of the next iteration.
+            // parameter slot, the other tap row or sh.enext before the top of the next iteration.  (The direct-sampling branch
+            // has had no barrier since the top of this iteration, where every thread reads sh.enext.)
+            if (oversampled) __syncthreads();
             if (tid == 0) {
                sh.par[cur ^ 1] = r_it;
                sh.enext = r_e;
