@@ -353,14 +353,14 @@ __global__ void __launch_bounds__(NT, DESC_MINB(BIN)) k_describe(const float *__
                }
                __syncthreads();
                if (staged) {
-                  const unsigned char *b0 = box - by0 * bw;
+                  const int off0 = -by0 * bw;      // (the column table already holds source column - bx0)
                   for (int t = tid; t < P * P; t += NT) {
                      const int jj = ha_div22(t, MP), xx = t - jj * P;
                      const float4 c = ctab[xx];
                      float wy = rtab[jj] + c.w;
                      const float fy = floorf(wy);
                      wy -= fy;
-                     const unsigned char *p = b0 + ((int)fy * bw + __float_as_int(c.x));
+                     const unsigned char *p = box + (off0 + (int)fy * bw + __float_as_int(c.x));
                      const float v = (1.0f - wy) * (c.z * (float)p[0] + c.y * (float)p[1]) + (wy) * (c.z * (float)p[bw] + c.y * (float)p[bw + 1]);
                      float *d = S + jj * PS + R + xx;
                      *d = v;
