@@ -105,6 +105,22 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(hesaff_b200.HesaffError, match="no CUDA device|CUDA"):
         hesaff_b200.AffineHessianDetector()
+    # the consumer entry point likewise: an error code, not a host computation
+    import ctypes as C
+    L = hesaff_b200.lib()
+    L.hesaff_match_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    buf = (C.c_char * 1024)()
+    rc = L.hesaff_match_descriptors(0, buf, 1, buf, 1, buf, buf, None, None)
+    assert rc < 0 and b"no CPU fallback" in L.hesaff_last_error()
+    # and the host program: exit code 2 with the library's message (the reference has no such path; a silent empty
+    # result would look like a valid run)
+    import subprocess
+    exe = os.path.join(ROOT, "hesaff_b200", "host", "hesaff")
+    if os.path.exists(exe):
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "tex_320x240_s11.pgm")], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 2 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
+        out = os.path.join(ROOT, "tests", "golden", "tex_320x240_s11.pgm.hesaff.sift")
+        assert not os.path.exists(out)
 
 
 def test_product_does_not_import_the_oracle():
